@@ -1,0 +1,347 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the equity hot path (BASELINE.json: "showdown evals/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg1] [--deal uniform|reference]
+    python bench.py --impl reference ...        # the reference's own C++ calculator on the host cores (oracle/_ref)
+    torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU)
+
+A "step" is one pass of the hot path over one batch of synthetic queries:
+  cfg3 (default, the configuration the metric is quoted on): 4,096 six-player flop queries x 10,000 trials per GPU
+       = 245.76 M showdown evals per step per GPU.  N GPUs: every rank owns its own 4,096 queries (weak scaling, no
+       data-path collective; queries keep global ids in the Philox counter).
+  cfg4: 169 starting-hand classes x 1,000,000 trials x 9 players, trials split over the ranks (strong scaling) and the
+       [169,2] win/tie counters all-reduced with NCCL inside the timed step.
+  cfg1: one heads-up preflop query x 10,000 trials (latency case).
+`value` = showdown evals (trials x players, all ranks) / device time of the K steps (CUDA events, max over ranks), with
+the queries already resident in HBM.  `e2e` = the same metric through the host-buffer API (equity_counts_batch ->
+npk_equity_host): queries start in host memory, H2D + kernels + D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "showdown_evals_per_s"
+UNIT = "showdown evals/s"
+
+
+def algorithmic_instr(players, known):
+    """integer thread-instructions one trial needs, A(P,b) = 64*ceil(D/8) + 8*D + 14*P + (P+3)."""
+    d = 2 * (players - 1) + (5 - known)
+    return 64 * -(-d // 8) + 8 * d + 14 * players + (players + 3)
+
+
+def workload(name):
+    if name == "cfg3":
+        return dict(name="cfg3: 4096 six-player flop queries x 10000 trials per GPU", queries=4096, trials=10000,
+                    players=6, known=3, shard="query")
+    if name == "cfg4":
+        return dict(name="cfg4: 169 starting-hand classes x 1000000 trials, 9 players, preflop", queries=169,
+                    trials=1000000, players=9, known=0, shard="trial")
+    if name == "cfg1":
+        return dict(name="cfg1: AsKs heads-up preflop x 10000 trials", queries=1, trials=10000, players=2, known=0,
+                    shard="query")
+    raise SystemExit("unknown workload " + name)
+
+
+def make_queries(wl, world, rank):
+    """Synthetic queries (numpy uint8).  cfg3: seed-0 torch generator, 5 distinct uniform cards per query."""
+    import numpy as np
+    import torch
+    q = wl["queries"]
+    if wl["name"].startswith("cfg3"):
+        g = torch.Generator().manual_seed(0)
+        cards = torch.rand(q * world, 52, generator=g).argsort(1)[:, :5].to(torch.uint8).numpy()
+        cards = cards[rank * q:(rank + 1) * q]
+        hole = cards[:, :2].copy()
+        board = np.full((q, 5), 255, dtype=np.uint8)
+        board[:, :3] = cards[:, 2:5]
+    elif wl["name"].startswith("cfg4"):
+        hole = []
+        for hi in range(13):
+            for lo in range(hi + 1):
+                if hi == lo:
+                    hole.append([4 * hi + 0, 4 * hi + 1])            # pair: xC xD
+                else:
+                    hole.append([4 * hi + 3, 4 * lo + 3])            # suited: xS yS
+                    hole.append([4 * hi + 3, 4 * lo + 2])            # offsuit: xS yH
+        hole = np.array(hole, dtype=np.uint8)
+        assert len(hole) == 169
+        board = np.full((169, 5), 255, dtype=np.uint8)
+    else:
+        hole = np.array([[51, 47]], dtype=np.uint8)
+        board = np.full((1, 5), 255, dtype=np.uint8)
+    npl = np.full(len(hole), wl["players"], dtype=np.uint8)
+    return hole, board, npl
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (NVML, 10 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_sample(wl, hole, board, npl, n_queries, threads):
+    """Time the reference's own C++ montecarlo() (oracle/_ref) on `n_queries` queries of the workload, `threads` threads."""
+    import oracle
+    hs = [[int(c) for c in hole[i % len(hole)]] for i in range(n_queries)]
+    bs = [[int(c) for c in board[i % len(board)] if c != 255] for i in range(n_queries)]
+    ps = [int(npl[i % len(npl)]) for i in range(n_queries)]
+    t0 = time.perf_counter()
+    eq = oracle.ref_montecarlo_batch(hs, bs, ps, wl["trials"], threads)
+    dt = time.perf_counter() - t0
+    assert all(0.0 <= e <= 1.0 for e in eq)
+    return n_queries * wl["trials"] * wl["players"] / dt, dt
+
+
+def port_sample(wl, hole, board, npl, n_queries):
+    """Fallback when oracle/_ref was never built: the C port of the same loop (oracle/npk_oracle.c), one thread."""
+    import oracle
+    t0 = time.perf_counter()
+    for i in range(n_queries):
+        oracle.mc_uniform([int(c) for c in hole[i % len(hole)]], [int(c) for c in board[i % len(board)] if c != 255],
+                          int(npl[i % len(npl)]), wl["trials"], 1 + i)
+    dt = time.perf_counter() - t0
+    return n_queries * wl["trials"] * wl["players"] / dt, dt
+
+
+def run_reference_arm(args, wl, rank):
+    if rank != 0:
+        return
+    import oracle
+    hole, board, npl = make_queries(wl, 1, 0)
+    cores = host_cores()
+    have_ref = oracle.ref_available()
+    if have_ref:
+        _, t1 = reference_sample(wl, hole, board, npl, 1, 1)
+    else:
+        _, t1 = port_sample(wl, hole, board, npl, 1)
+    budget = 150.0
+    n = int(max(1, min(4 * cores, budget * (cores if have_ref else 1) / ((args.steps + args.warmup) * t1))))
+    n = min(n, max(1, wl["queries"]))
+    times = []
+    for i in range(args.warmup + args.steps):
+        if have_ref:
+            _, dt = reference_sample(wl, hole, board, npl, n, cores)
+        else:
+            _, dt = port_sample(wl, hole, board, npl, n)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n * wl["trials"] * wl["players"] * args.steps / total
+    sample = "%d of the workload's %d queries x %d trials per step" % (n, wl["queries"], wl["trials"])
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int", "data": "synthetic",
+            "config": {"workload": wl["name"], "players": wl["players"], "known_board_cards": wl["known"],
+                       "trials": wl["trials"], "deal_mode": "uniform", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if have_ref else 1,
+                             "kind": "reference" if have_ref else "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--deal", default="uniform", choices=["uniform", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = workload(args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import neuron_poker_b200 as npk
+    from neuron_poker_b200 import _lib
+    import ctypes
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    os.environ["NPK_DEVICE"] = str(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _lib.ensure_init(local_rank)
+
+    hole_h, board_h, npl_h = make_queries(wl, world, rank)
+    Q, T, P, B = len(hole_h), wl["trials"], wl["players"], wl["known"]
+    hole, board, npl = (torch.as_tensor(x).to(dev) for x in (hole_h, board_h, npl_h))
+    by_trial = wl["shard"] == "trial" and world > 1
+    t_off, t_cnt = npk.dist.trial_shard(T, rank, world) if by_trial else (0, T)
+    q_off = 0 if wl["shard"] == "trial" else rank * Q
+    out = {"wins": torch.zeros(Q, dtype=torch.int64, device=dev), "ties": torch.zeros(Q, dtype=torch.int64, device=dev)}
+    both = torch.zeros((Q, 2), dtype=torch.int64, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    # integer-issue peak of this GPU, measured in this run (roofline denominator)
+    peak = 0.0
+    peak_detail = {}
+    for variant, nm in ((0, "lop3"), (1, "imad"), (2, "imad+lop3")):
+        v = ctypes.c_double(0)
+        ms = ctypes.c_float(0)
+        _lib.check(L.npk_int_peak(variant, 2000, ctypes.byref(v), ctypes.byref(ms)))
+        peak_detail[nm] = v.value / 1e12
+        peak = max(peak, v.value)
+
+    def step(i):
+        if by_trial:
+            # the kernel accumulates into two contiguous [Q] counters; they are packed into one [Q,2] tensor so a
+            # single all-reduce combines the ranks' trial ranges
+            o = {"wins": out["wins"].zero_(), "ties": out["ties"].zero_()}
+            npk.get_equity_batch(hole, board, npl, t_cnt, seed_value=1000 + i, deal_mode=args.deal, trial_offset=t_off,
+                                 uniform_shape=(P, B), validate=False, out=o)
+            torch.stack([o["wins"], o["ties"]], 1, out=both)
+            npk.dist.allreduce_counts(both)
+        else:
+            out["wins"].zero_(); out["ties"].zero_()
+            npk.get_equity_batch(hole, board, npl, T, seed_value=1000 + i, deal_mode=args.deal, query_offset=q_off,
+                                 uniform_shape=(P, B), validate=False, out=out)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)                      # evict L2 between timed steps (outside the events)
+        starts[i].record()
+        step(args.warmup + i)
+        ends[i].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    check_eq = float((out["wins"] + out["ties"]).double().mean().item() / (T if not by_trial else T)) if not by_trial \
+        else float((both[:, 0] + both[:, 1]).double().mean().item() / T)
+
+    evals_per_step = Q * T * P * (1 if by_trial else world)      # whole job, all ranks
+    value = evals_per_step * args.steps / (dev_ms * 1e-3)
+
+    # end to end through the host-buffer API: queries in host memory, counters back in host memory, every step
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(2):
+        npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5000 + i, deal_mode=args.deal)
+    if world > 1:
+        dist.barrier()
+    e0 = time.perf_counter()
+    for i in range(e2e_steps):
+        r = npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=args.deal)
+    e2e_s = time.perf_counter() - e0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = Q * t_cnt * P * world * e2e_steps / e2e_s
+
+    a_instr = algorithmic_instr(P, B)
+    kernel_ms = dev_ms / args.steps
+    achieved = Q * t_cnt * a_instr / (kernel_ms * 1e-3)          # per GPU
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if by_trial else "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": wl["name"], "queries_per_gpu": Q, "trials": T, "players": P, "known_board_cards": B,
+                   "deal_mode": args.deal, "sharding": ("trial ranges + NCCL all-reduce of [Q,2] counters" if by_trial
+                                                        else "query blocks, no collective"),
+                   "l2": "flushed (256 MiB fill) between timed steps; inputs are 28 KB", "mean_equity": check_eq,
+                   "wall_s_timed_loop": wall},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * Q), "d2h_bytes_per_step": int(16 * Q),
+                "steps": e2e_steps, "api": "neuron_poker_b200.equity_counts_batch -> npk_equity_host"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tthread-instr/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_reference_kernel",
+                     "algorithmic_instr_per_trial": a_instr, "peak_source": "npk_int_peak measured in this run",
+                     "peak_variants": peak_detail, "nominal_issue_peak": 148 * 128 * 1.965e9 / 1e12},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = host_cores()
+        if oracle.ref_available():
+            n = min(max(1, Q), 2 * cores)
+            v, dt = reference_sample(wl, hole_h, board_h, npl_h, n, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": "%d queries x %d trials through the reference C++ montecarlo() "
+                                              "(oracle/_ref), %d threads, %.1f s" % (n, T, cores, dt)}
+        else:
+            v, dt = port_sample(wl, hole_h, board_h, npl_h, 2)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "2 queries x %d trials through oracle/npk_oracle.c, %.1f s" % (T, dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

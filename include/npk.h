@@ -1,0 +1,131 @@
+/*
+ * npk.h -- C ABI of libnpk.so, the B200-native replacement for neuron_poker's Monte-Carlo equity hot path.
+ *
+ * This is the boundary a host-language binding targets (ctypes today; pybind11 / cgo / JNI would bind the same
+ * symbols).  Plain pointers and sizes only, no torch or C++ types.  Unless a function says "host", every pointer is a
+ * DEVICE pointer owned by the caller (e.g. torch tensors), nothing is allocated per call, and work is enqueued on the
+ * caller's CUDA stream (`stream` is a cudaStream_t passed as void*, NULL = default stream) without synchronising.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference repository root):
+ *   npk_equity_batch    MonteCarlo.run_montecarlo's trial loop   tools/montecarlo_python.py:191-252 (dealing :121-189)
+ *                       and montecarlo()                          tools/montecarlo_cpp/Montecarlo.cpp:240-259,
+ *                       i.e. what get_equity (montecarlo_python.py:401-406) and the pybind11 export
+ *                       pymontecarlo.montecarlo (tools/montecarlo_cpp/pymontecarlo.cpp:21-23) compute, batched
+ *   npk_equity_host     the same, for HOST buffers: one blocking call = one (batch of) get_equity call(s)
+ *   npk_rank7_batch     _calc_score ordering                      tools/hand_evaluator.py:27-119
+ *   npk_showdown_batch  get_winner / eval_best_hand               tools/hand_evaluator.py:9-24 (used by gym_env/env.py:576-593)
+ *   npk_enum_batch      no counterpart (the reference only samples); exact enumeration used for bit-exact checks
+ *
+ * Cards are bytes: id = 4*rank + suit with ranks "23456789TJQKA" and suits "CDHS" -- the order of
+ * MonteCarlo.create_card_deck (tools/montecarlo_python.py:114-119).  0xFF marks "no card" in board arrays.
+ * Hand strength is a rank id in [0, 5034): the index of the reference's (score, card_ranks) tuple among all distinct
+ * 7-card tuples in ascending order, so ids compare exactly like the reference's tuples (ties <=> equal ids).
+ *
+ * All functions return 0 on success or a negative NPK_ERR_* code; npk_last_error() gives a message (thread-local).
+ */
+#ifndef NPK_H
+#define NPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NPK_OK 0
+#define NPK_ERR_NOT_INITIALIZED (-1)
+#define NPK_ERR_INVALID_ARGUMENT (-2)
+#define NPK_ERR_CUDA (-3)
+#define NPK_ERR_TABLES (-4)
+#define NPK_ERR_INVALID_CARDS (-5)   /* card id >= 52, duplicate cards, board with holes, players outside 1..10 */
+
+/* dealing semantics */
+#define NPK_DEAL_UNIFORM 0   /* uniform without replacement = the C++ sibling's std::shuffle (Montecarlo.cpp:293-312)   */
+#define NPK_DEAL_REFERENCE 1 /* the Python reference's dealer incl. its bias (montecarlo_python.py:165-189) */
+
+/* flags for npk_equity_batch */
+#define NPK_FLAG_VALIDATE 1u /* check card ids / duplicates on the device and sync once to report NPK_ERR_INVALID_CARDS */
+
+#define NPK_NUM_CLASSES 5034
+#define NPK_NUM_HAND_TYPES 9
+
+/* Build the rank tables on the host and upload them to `device`; selects that device for later calls of this thread.
+ * Idempotent per device.  Fails (NPK_ERR_CUDA) when no usable GPU is present: there is no CPU fallback. */
+int npk_init(int device);
+/* Build the tables on the host only (no GPU needed): enough for npk_get_tables / npk_host_rank7. */
+int npk_init_host_tables(void);
+/* Make an initialised `device` current for this thread's later calls (cheap; call it when switching GPUs). */
+int npk_set_device(int device);
+int npk_shutdown(void);
+const char* npk_last_error(void);
+int npk_sm_count(void);
+
+/* Copies of the host-built tables (any pointer may be NULL).  value: row-displaced rank ids (n_value entries),
+ * rowoff: 8192 row offsets, flush: 8192 entries by flush-suit rank mask, desc: 52 card descriptors,
+ * type_start: 10 entries (first rank id of each hand type + end), class_keys: 5034 order keys. */
+int npk_get_tables(uint16_t* value, int64_t* n_value, uint16_t* rowoff, uint16_t* flush, uint32_t* desc,
+                   uint16_t* type_start, uint64_t* class_keys);
+/* HOST: evaluate hands through the host copy of the tables (table self-check, not a compute path). */
+int npk_host_rank7(const uint8_t* cards /*[n,7] host*/, int64_t n, uint16_t* ranks /*[n] host*/);
+
+/* Bytes of device workspace npk_equity_batch needs for Q queries. */
+int64_t npk_equity_workspace_bytes(int64_t Q);
+
+/*
+ * Monte-Carlo equity for Q queries x `trials` trials each.
+ *   hole       [Q,2]  hero cards
+ *   board      [Q,5]  known table cards first, 0xFF padding (0..5 known cards)
+ *   n_players  [Q]    players still in the hand including the hero (1..10)
+ *   uniform_players / uniform_known: if >= 0, EVERY query has that many players / known board cards and the call is
+ *                     fully asynchronous; if either is < 0 the queries are classified on the device, which costs one
+ *                     small device->host read (the stream is synchronised once) before the per-shape launches.
+ *   seed, trial_offset, query_offset: trial t of query q uses the Philox4x32-10 stream with counter
+ *                     (t + trial_offset, q + query_offset) and key = seed: results do not depend on how trials or
+ *                     queries are partitioned over calls or GPUs.
+ *   wins_strict, ties [Q] u64, ACCUMULATED into (caller zeroes them): hero strictly best / tied for best.
+ *                     reference equity = (wins_strict + ties) / trials  (ties count as wins, montecarlo_python.py:223-229)
+ *   win_types  [Q,9] u64 or NULL: hand type of the hero whenever he wins or ties (winnerCardTypeList, :230-231, :244-248)
+ *   passes     [Q] u64 or NULL: REFERENCE mode only, opponent draw attempts (`passes`, :167)
+ *   workspace  npk_equity_workspace_bytes(Q) bytes of device memory, private to this call until it completes
+ */
+int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                     int uniform_players, int uniform_known, uint64_t seed, int64_t trial_offset, int64_t query_offset,
+                     int deal_mode, uint32_t flags, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
+                     void* workspace, void* stream);
+
+/* HOST buffers in, HOST buffers out: copies the queries to the device (pinned staging owned by the library), runs
+ * npk_equity_batch with validation, copies the counters back and returns when they are valid.  wins/ties (and the
+ * optional win_types [Q,9], passes [Q]) are overwritten. */
+int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                    uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
+                    uint64_t* passes);
+
+/* rank ids of N 7-card hands */
+int npk_rank7_batch(const uint8_t* cards /*[N,7]*/, int64_t N, uint16_t* ranks /*[N]*/, void* stream);
+/* rank ids of the 7-card hands number first..first+count-1 in colexicographic order of C(52,7) = 133,784,560 hands
+ * (c0<...<c6, index = sum C(c_i, i+1)) -- no input traffic; for the exhaustive parity check */
+int npk_rank7_colex(int64_t first, int64_t count, uint16_t* ranks, void* stream);
+
+/* Exact enumeration: heads-up (n_players = 2) with 0..5 known board cards, or three players on a complete board.
+ * win/tie/lose [Q] u64 are overwritten: hero strictly best / tied / beaten, over all completions x opponent hands
+ * (ordered pairs of disjoint hands for three players). */
+int npk_enum_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, uint64_t* win,
+                   uint64_t* tie, uint64_t* lose, void* stream);
+
+/* Batched showdown: holes [N,maxp,2], n_players [N] (1..maxp), board [N,5] complete.  winner [N] = first index among the
+ * best hands (hand_evaluator.py:23 stable sort), wtype [N] = its hand type 0..8, ranks [N,maxp] or NULL. */
+int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uint8_t* board, int64_t N, int maxp,
+                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, void* stream);
+
+/* Integer-issue microbenchmark on the current device (the roofline denominator of the Monte-Carlo kernel):
+ * variant 0 = LOP3 chains (alu pipe), 1 = IMAD chains (fma pipe), 2 = both interleaved.  Reports executed
+ * thread-instructions per second (best of 3 timed launches after a warm-up) and that launch's duration. */
+int npk_int_peak(int variant, int iters, double* thread_instr_per_s, float* ms);
+
+/* Philox4x32-10 known-answer hook: out[4i..4i+3] = philox(counter ctr[4i..4i+3], key (k0,k1)) */
+int npk_philox_debug(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPK_H */

@@ -1,0 +1,78 @@
+"""ctypes binding of libnpk.so (include/npk.h).  The library is the product: if it (or a GPU) is missing every compute
+entry point raises -- there is no CPU fallback."""
+import ctypes
+import os
+import threading
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+_inited = set()
+
+NPK_DEAL_UNIFORM = 0
+NPK_DEAL_REFERENCE = 1
+NPK_FLAG_VALIDATE = 1
+ERRORS = {-1: "NPK_ERR_NOT_INITIALIZED", -2: "NPK_ERR_INVALID_ARGUMENT", -3: "NPK_ERR_CUDA", -4: "NPK_ERR_TABLES",
+          -5: "NPK_ERR_INVALID_CARDS"}
+
+
+class NpkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERRORS.get(code, code), msg))
+        self.code = code
+
+
+def lib():
+    """Load (building it first if the sources are newer) neuron_poker_b200/libnpk.so."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                path = _build.LIB
+                if not os.path.exists(path) or (_build.stale() and os.environ.get("NPK_NO_REBUILD") != "1"):
+                    path = _build.build()
+                L = ctypes.CDLL(path)
+                vp, u8, u16, u32, u64, i64, i32 = (ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int)
+                L.npk_last_error.restype = ctypes.c_char_p
+                L.npk_init.argtypes = [i32]
+                L.npk_set_device.argtypes = [i32]
+                L.npk_get_tables.argtypes = [u16, ctypes.POINTER(ctypes.c_int64), u16, u16, u32, u16, u64]
+                L.npk_host_rank7.argtypes = [u8, i64, u16]
+                L.npk_equity_workspace_bytes.argtypes = [i64]
+                L.npk_equity_workspace_bytes.restype = i64
+                L.npk_equity_batch.argtypes = [u8, u8, u8, i64, i64, i32, i32, ctypes.c_uint64, i64, i64, i32,
+                                               ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
+                L.npk_equity_host.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, i32, u64, u64, u64, u64]
+                L.npk_rank7_batch.argtypes = [u8, i64, u16, vp]
+                L.npk_rank7_colex.argtypes = [i64, i64, u16, vp]
+                L.npk_enum_batch.argtypes = [u8, u8, u8, i64, u64, u64, u64, vp]
+                L.npk_showdown_batch.argtypes = [u8, u8, u8, i64, i32, vp, u8, u16, vp]
+                L.npk_int_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)]
+                L.npk_philox_debug.argtypes = [u32, ctypes.c_uint32, ctypes.c_uint32, i32, u32, vp]
+                _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise NpkError(rc, lib().npk_last_error().decode())
+    return rc
+
+
+def init(device=0):
+    """npk_init(device): build + upload the rank tables; raises NpkError when no B200 is usable."""
+    L = lib()
+    check(L.npk_init(int(device)))
+    _inited.add(int(device))
+    return L
+
+
+def ensure_init(device=0):
+    """Initialise `device` on first use and make it current for this thread inside libnpk's CUDA runtime."""
+    if int(device) not in _inited:
+        return init(device)
+    L = lib()
+    check(L.npk_set_device(int(device)))
+    return L

@@ -1,0 +1,549 @@
+// npk_capi.cu -- the C ABI declared in include/npk.h: table upload, query classification, kernel launches.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/npk.h"
+#include "npk_kernels.h"
+#include "npk_tables.h"
+
+static_assert(npk::kDevDescShift == npk::kDescShift && npk::kRowBits == npk::kRowShift,
+              "device and host table geometry differ");
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+
+struct DeviceState {
+    bool ready = false;
+    int sm_count = 0;
+    npk::DeviceTables t{};
+    void* blob = nullptr;
+};
+
+npk::Tables g_tables;
+bool g_tables_ready = false;
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+
+// host-staging state of npk_equity_host (one per process, guarded by g_host_mu)
+std::mutex g_host_mu;
+struct HostStage {
+    int device = -1;
+    int64_t cap_q = 0;
+    uint8_t* h_in = nullptr;      // pinned: hole[2Q] board[5Q] players[Q]
+    uint64_t* h_out = nullptr;    // pinned: wins[Q] ties[Q] types[9Q] passes[Q]
+    uint8_t* d_in = nullptr;
+    uint64_t* d_out = nullptr;
+    void* d_ws = nullptr;
+    cudaStream_t stream = nullptr;
+} g_stage;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(NPK_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int ensure_host_tables()
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_tables_ready) return NPK_OK;
+    const char* err = npk::build_tables(g_tables);
+    if (err && err[0]) return fail(NPK_ERR_TABLES, std::string("table construction failed: ") + err);
+    g_tables_ready = true;
+    return NPK_OK;
+}
+
+int current_state(DeviceState** out)
+{
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= kMaxDevices || !g_dev[dev].ready)
+        return fail(NPK_ERR_NOT_INITIALIZED, "npk_init(device) has not been called for the current CUDA device");
+    *out = &g_dev[dev];
+    return NPK_OK;
+}
+
+// ---- query classification (mixed player counts / board sizes) --------------------------------------------------------
+// workspace layout (bytes): [0,512) 64 work counters u64 | [512,768) 64 group counts u32 | [768,1024) 64 cursors u32
+//                           | [1024,1028) invalid-query count | [2048, 2048+4Q) qindex
+constexpr int kWsCounters = 0, kWsCounts = 512, kWsCursors = 768, kWsInvalid = 1024, kWsIndex = 2048;
+constexpr int kGroups = 60;   // group = nopp * 6 + known, nopp 0..9, known 0..5
+
+__device__ __forceinline__ int classify_query(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
+                                              long long q)
+{
+    const int np = n_players[q];
+    unsigned long long mask = 0;
+    int known = 0, bad = 0;
+    bool ended = false;
+    for (int i = 0; i < 2; i++) {
+        const int c = hole[2 * q + i];
+        if (c >= 52) bad = 1; else { bad |= (int)(mask >> c & 1ull); mask |= 1ull << c; }
+    }
+    for (int i = 0; i < 5; i++) {
+        const int c = board[5 * q + i];
+        if (c == 0xFF) { ended = true; continue; }
+        if (ended || c >= 52) { bad = 1; continue; }
+        bad |= (int)(mask >> c & 1ull);
+        mask |= 1ull << c;
+        known++;
+    }
+    if (np < 1 || np > 10) bad = 1;
+    return bad ? -1 : (np - 1) * 6 + known;
+}
+
+__global__ void classify_count_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
+                                      uint8_t* ws)
+{
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + kWsCounts);
+    uint32_t* invalid = reinterpret_cast<uint32_t*>(ws + kWsInvalid);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
+        const int g = classify_query(hole, board, n_players, q);
+        if (g < 0) atomicAdd(invalid, 1u); else atomicAdd(&counts[g], 1u);
+    }
+}
+
+struct GroupOffsets { uint32_t off[64]; };
+
+__global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
+                                     uint8_t* ws, GroupOffsets go)
+{
+    uint32_t* cursors = reinterpret_cast<uint32_t*>(ws + kWsCursors);
+    int32_t* qindex = reinterpret_cast<int32_t*>(ws + kWsIndex);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
+        const int g = classify_query(hole, board, n_players, q);
+        if (g < 0) continue;
+        qindex[go.off[g] + atomicAdd(&cursors[g], 1u)] = (int32_t)q;
+    }
+}
+
+// players == 1: the hero is the only hand and always "wins" (reference: index 0 is the best of one hand)
+__global__ void solo_fill_kernel(const int32_t* qindex, long long nq, long long trials, unsigned long long* wins)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&wins[qindex ? qindex[i] : i], (unsigned long long)trials);
+}
+
+uint32_t pick_chunk(long long trials)
+{
+    if (trials <= 1024) return (uint32_t)(trials > 0 ? trials : 1);
+    return 1024;
+}
+
+int grid_for(const DeviceState& ds, long long items, int warps_per_cta)
+{
+    long long ctas = (items + warps_per_cta - 1) / warps_per_cta;
+    if (ctas < 1) ctas = 1;
+    if (ctas > ds.sm_count) ctas = ds.sm_count;
+    return (int)ctas;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* npk_last_error(void) { return g_err.c_str(); }
+
+int npk_init_host_tables(void) { return ensure_host_tables(); }
+
+int npk_init(int device)
+{
+    int rc = ensure_host_tables();
+    if (rc) return rc;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(NPK_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count || device >= kMaxDevices) return fail(NPK_ERR_INVALID_ARGUMENT, "bad device index");
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceState& ds = g_dev[device];
+    if (ds.ready) return NPK_OK;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10)
+        return fail(NPK_ERR_CUDA, "libnpk is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+                                      std::to_string(prop.minor));
+    ds.sm_count = prop.multiProcessorCount;
+
+    const size_t vb = (g_tables.value.size() * 2 + 15) & ~size_t(15);
+    const size_t rb = g_tables.row_offset.size() * 2, fb = g_tables.flush.size() * 2, db = 52 * 4;
+    std::vector<uint8_t> blob(vb + rb + fb + 256, 0);
+    std::memcpy(blob.data(), g_tables.value.data(), g_tables.value.size() * 2);
+    std::memcpy(blob.data() + vb, g_tables.row_offset.data(), rb);
+    std::memcpy(blob.data() + vb + rb, g_tables.flush.data(), fb);
+    uint32_t desc[52];
+    for (int c = 0; c < 52; c++) desc[c] = npk::card_desc(c);
+    std::memcpy(blob.data() + vb + rb + fb, desc, db);
+    e = cudaMalloc(&ds.blob, blob.size());
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(tables)");
+    e = cudaMemcpy(ds.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tables)");
+    uint8_t* b = static_cast<uint8_t*>(ds.blob);
+    ds.t.value = reinterpret_cast<const uint16_t*>(b);
+    ds.t.rowoff = reinterpret_cast<const uint16_t*>(b + vb);
+    ds.t.flush = reinterpret_cast<const uint16_t*>(b + vb + rb);
+    ds.t.desc = reinterpret_cast<const uint32_t*>(b + vb + rb + fb);
+    ds.t.value_bytes = (uint32_t)vb;
+    ds.t.rowoff_bytes = (uint32_t)rb;
+    ds.t.flush_bytes = (uint32_t)fb;
+    for (int i = 0; i < 10; i++) ds.t.type_start[i] = g_tables.type_start[i];
+    ds.ready = true;
+    return NPK_OK;
+}
+
+int npk_set_device(int device)
+{
+    if (device < 0 || device >= kMaxDevices || !g_dev[device].ready)
+        return fail(NPK_ERR_NOT_INITIALIZED, "npk_init(device) has not been called for this device");
+    cudaError_t e = cudaSetDevice(device);
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "cudaSetDevice");
+}
+
+int npk_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (int d = 0; d < kMaxDevices; d++) {
+        if (!g_dev[d].ready) continue;
+        cudaSetDevice(d);
+        cudaFree(g_dev[d].blob);
+        g_dev[d] = DeviceState{};
+    }
+    std::lock_guard<std::mutex> lk2(g_host_mu);
+    if (g_stage.device >= 0) {
+        cudaSetDevice(g_stage.device);
+        cudaFreeHost(g_stage.h_in); cudaFreeHost(g_stage.h_out);
+        cudaFree(g_stage.d_in); cudaFree(g_stage.d_out); cudaFree(g_stage.d_ws);
+        if (g_stage.stream) cudaStreamDestroy(g_stage.stream);
+        g_stage = HostStage{};
+    }
+    return NPK_OK;
+}
+
+int npk_sm_count(void)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    return rc ? rc : ds->sm_count;
+}
+
+int npk_get_tables(uint16_t* value, int64_t* n_value, uint16_t* rowoff, uint16_t* flush, uint32_t* desc,
+                   uint16_t* type_start, uint64_t* class_keys)
+{
+    int rc = ensure_host_tables();
+    if (rc) return rc;
+    if (n_value) *n_value = (int64_t)g_tables.value.size();
+    if (value) std::memcpy(value, g_tables.value.data(), g_tables.value.size() * 2);
+    if (rowoff) std::memcpy(rowoff, g_tables.row_offset.data(), g_tables.row_offset.size() * 2);
+    if (flush) std::memcpy(flush, g_tables.flush.data(), g_tables.flush.size() * 2);
+    if (desc) for (int c = 0; c < 52; c++) desc[c] = npk::card_desc(c);
+    if (type_start) for (int i = 0; i < 10; i++) type_start[i] = g_tables.type_start[i];
+    if (class_keys) std::memcpy(class_keys, g_tables.class_key.data(), g_tables.class_key.size() * 8);
+    return NPK_OK;
+}
+
+int npk_host_rank7(const uint8_t* cards, int64_t n, uint16_t* ranks)
+{
+    int rc = ensure_host_tables();
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 7; k++)
+            if (cards[7 * i + k] >= 52) return fail(NPK_ERR_INVALID_CARDS, "card id >= 52");
+        ranks[i] = npk::host_rank7(g_tables, cards + 7 * i);
+    }
+    return NPK_OK;
+}
+
+int64_t npk_equity_workspace_bytes(int64_t Q) { return kWsIndex + 4 * (Q > 0 ? Q : 0) + 64; }
+
+int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                     int uniform_players, int uniform_known, uint64_t seed, int64_t trial_offset, int64_t query_offset,
+                     int deal_mode, uint32_t flags, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
+                     void* workspace, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q < 0 || trials < 0 || trial_offset < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (Q == 0 || trials == 0) return NPK_OK;
+    if (Q > 0x7fffffffLL) return fail(NPK_ERR_INVALID_ARGUMENT, "at most 2^31-1 queries per call");
+    if (!hole || !board || !n_players || !wins_strict || !ties || !workspace)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+    const bool uniform_shape = uniform_players >= 0 && uniform_known >= 0;
+    if (uniform_shape && (uniform_players < 1 || uniform_players > 10 || uniform_known > 5))
+        return fail(NPK_ERR_INVALID_CARDS, "players must be 1..10 and known board cards 0..5");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    cudaError_t e = cudaMemsetAsync(ws, 0, kWsIndex, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+
+    npk::EquityParams p{};
+    p.tables = ds->t;
+    p.hole = hole; p.board = board; p.n_players = n_players;
+    p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.chunk = pick_chunk(trials);
+    p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
+    p.ties = reinterpret_cast<unsigned long long*>(ties);
+    p.win_types = reinterpret_cast<unsigned long long*>(win_types);
+    p.passes = deal_mode == NPK_DEAL_REFERENCE ? reinterpret_cast<unsigned long long*>(passes) : nullptr;
+    const long long chunks = (trials + p.chunk - 1) / p.chunk;
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+
+    uint32_t counts[64];
+    std::memset(counts, 0, sizeof counts);
+    const bool need_classes = !uniform_shape || (flags & NPK_FLAG_VALIDATE);
+    if (need_classes) {
+        const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
+        classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
+        uint32_t host[64 + 64 + 1];
+        e = cudaMemcpyAsync(host, ws + kWsCounts, 4 * 129, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail(e, "query classification");
+        if (host[128]) return fail(NPK_ERR_INVALID_CARDS, std::to_string(host[128]) +
+                                   " invalid quer" + (host[128] == 1 ? "y" : "ies") +
+                                   " (card id >= 52, duplicate cards, gap in the board, or players outside 1..10)");
+        std::memcpy(counts, host, sizeof counts);
+        if (uniform_shape && counts[(uniform_players - 1) * 6 + uniform_known] != (uint32_t)Q)
+            return fail(NPK_ERR_INVALID_ARGUMENT, "queries do not all have the declared uniform shape");
+    }
+
+    if (deal_mode == NPK_DEAL_REFERENCE) {
+        // the reference-dealer kernel is generic in players / board size: one launch over all queries
+        if (uniform_shape && uniform_players == 1) {
+            solo_fill_kernel<<<(int)std::min<long long>((Q + 255) / 256, 1024), 256, 0, s>>>(nullptr, Q, trials, p.wins);
+            return NPK_OK;
+        }
+        p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
+        e = npk::launch_equity_reference(p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
+        if (e != cudaSuccess) return cuda_fail(e, "equity_reference_kernel launch");
+        return NPK_OK;
+    }
+
+    const size_t smem = npk::equity_uniform_smem(ds->t);
+    if (uniform_shape) {
+        if (uniform_players == 1) {
+            solo_fill_kernel<<<(int)std::min<long long>((Q + 255) / 256, 1024), 256, 0, s>>>(nullptr, Q, trials, p.wins);
+            return NPK_OK;
+        }
+        p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
+        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p,
+                                       grid_for(*ds, Q * chunks, npk::kEquityThreads / 32), smem, s);
+        if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
+        return NPK_OK;
+    }
+
+    GroupOffsets go;
+    uint32_t acc = 0;
+    for (int g = 0; g < 64; g++) { go.off[g] = acc; acc += counts[g]; }
+    {
+        const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
+        classify_fill_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws, go);
+    }
+    const int32_t* qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
+    for (int g = 0; g < kGroups; g++) {
+        if (!counts[g]) continue;
+        const int nopp = g / 6, known = g % 6;
+        p.qindex = qindex + go.off[g]; p.nq = counts[g]; p.work_counter = counters + g;
+        if (nopp == 0) {
+            solo_fill_kernel<<<(int)std::min<long long>((p.nq + 255) / 256, 1024), 256, 0, s>>>(p.qindex, p.nq, trials, p.wins);
+            continue;
+        }
+        e = npk::launch_equity_uniform(nopp, 5 - known, p, grid_for(*ds, p.nq * chunks, npk::kEquityThreads / 32), smem, s);
+        if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
+    }
+    return NPK_OK;
+}
+
+int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                    uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
+                    uint64_t* passes)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
+    if (!hole || !board || !n_players || !wins_strict || !ties) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    HostStage& st = g_stage;
+    cudaError_t e;
+    if (st.device != dev || st.cap_q < Q) {
+        if (st.device >= 0) {
+            cudaSetDevice(st.device);
+            cudaFreeHost(st.h_in); cudaFreeHost(st.h_out); cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_ws);
+            if (st.stream) cudaStreamDestroy(st.stream);
+            cudaSetDevice(dev);
+        }
+        st = HostStage{};
+        const int64_t cap = Q < 1024 ? 1024 : Q;
+        if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        if ((e = cudaMallocHost(&st.h_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        if ((e = cudaMallocHost(&st.h_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        if ((e = cudaMalloc(&st.d_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&st.d_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&st.d_ws, npk_equity_workspace_bytes(cap))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        st.device = dev; st.cap_q = cap;
+    }
+    std::memcpy(st.h_in, hole, 2 * Q);
+    std::memcpy(st.h_in + 2 * Q, board, 5 * Q);
+    std::memcpy(st.h_in + 7 * Q, n_players, Q);
+    // a uniform shape lets the call run without the classification round trip; validate on the host instead
+    int up = n_players[0], uk = 0;
+    for (int i = 0; i < 5; i++) uk += board[i] != 0xFF;
+    bool uniform = true;
+    for (int64_t q = 0; q < Q; q++) {
+        unsigned long long mask = 0;
+        int known = 0;
+        bool ended = false, bad = n_players[q] < 1 || n_players[q] > 10;
+        for (int i = 0; i < 2; i++) {
+            const int c = hole[2 * q + i];
+            if (c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
+            mask |= 1ull << c;
+        }
+        for (int i = 0; i < 5 && !bad; i++) {
+            const int c = board[5 * q + i];
+            if (c == 0xFF) { ended = true; continue; }
+            if (ended || c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
+            mask |= 1ull << c;
+            known++;
+        }
+        if (bad) return fail(NPK_ERR_INVALID_CARDS, "query " + std::to_string(q) +
+                             ": card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+        if (n_players[q] != up || known != uk) uniform = false;
+    }
+    const size_t n_out = (size_t)Q * 12;
+    if ((e = cudaMemcpyAsync(st.d_in, st.h_in, 8 * Q, cudaMemcpyHostToDevice, st.stream)) != cudaSuccess) return cuda_fail(e, "H2D");
+    if ((e = cudaMemsetAsync(st.d_out, 0, 8 * n_out, st.stream)) != cudaSuccess) return cuda_fail(e, "memset");
+    uint64_t* d_wins = st.d_out;
+    uint64_t* d_ties = st.d_out + Q;
+    uint64_t* d_types = st.d_out + 2 * Q;
+    uint64_t* d_pass = st.d_out + 11 * Q;
+    rc = npk_equity_batch(st.d_in, st.d_in + 2 * Q, st.d_in + 7 * Q, Q, trials, uniform ? up : -1, uniform ? uk : -1, seed,
+                          0, 0, deal_mode, 0, d_wins, d_ties, win_types ? d_types : nullptr, passes ? d_pass : nullptr,
+                          st.d_ws, st.stream);
+    if (rc) return rc;
+    const size_t n_copy = passes ? 12 * Q : (win_types ? 11 * Q : 2 * Q);
+    if ((e = cudaMemcpyAsync(st.h_out, st.d_out, 8 * n_copy, cudaMemcpyDeviceToHost, st.stream)) != cudaSuccess) return cuda_fail(e, "D2H");
+    if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernels");
+    std::memcpy(wins_strict, st.h_out, 8 * Q);
+    std::memcpy(ties, st.h_out + Q, 8 * Q);
+    if (win_types) std::memcpy(win_types, st.h_out + 2 * Q, 8 * 9 * Q);
+    if (passes) std::memcpy(passes, st.h_out + 11 * Q, 8 * Q);
+    return NPK_OK;
+}
+
+int npk_rank7_batch(const uint8_t* cards, int64_t N, uint16_t* ranks, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    cudaError_t e = npk::launch_rank7(ds->t, cards, N, ranks, grid_for(*ds, (N + 31) / 32, npk::kAuxThreads / 32),
+                                      static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "rank7_kernel launch");
+}
+
+int npk_rank7_colex(int64_t first, int64_t count, uint16_t* ranks, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (first < 0 || count < 0 || first + count > 133784560LL) return fail(NPK_ERR_INVALID_ARGUMENT, "range outside C(52,7)");
+    if (count == 0) return NPK_OK;
+    cudaError_t e = npk::launch_rank7_colex(ds->t, first, count, ranks, grid_for(*ds, (count + 31) / 32, npk::kAuxThreads / 32),
+                                            static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "rank7_colex_kernel launch");
+}
+
+int npk_enum_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, uint64_t* win,
+                   uint64_t* tie, uint64_t* lose, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
+    npk::EnumParams p{};
+    p.tables = ds->t; p.hole = hole; p.board = board; p.n_players = n_players; p.nq = Q;
+    p.win = reinterpret_cast<unsigned long long*>(win);
+    p.tie = reinterpret_cast<unsigned long long*>(tie);
+    p.lose = reinterpret_cast<unsigned long long*>(lose);
+    const int grid = (int)std::min<long long>(Q, ds->sm_count);
+    cudaError_t e = npk::launch_enum(p, grid, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "enum_kernel launch");
+}
+
+int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uint8_t* board, int64_t N, int maxp,
+                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (maxp < 1 || maxp > 23) return fail(NPK_ERR_INVALID_ARGUMENT, "maxp must be 1..23");
+    cudaError_t e = npk::launch_showdown(ds->t, holes, n_players, board, N, maxp, winner, wtype, ranks,
+                                         grid_for(*ds, (N + 31) / 32, npk::kAuxThreads / 32), static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "showdown_kernel launch");
+}
+
+int npk_int_peak(int variant, int iters, double* thread_instr_per_s, float* ms_out)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (variant < 0 || variant > 2 || iters < 1) return fail(NPK_ERR_INVALID_ARGUMENT, "variant 0..2, iters >= 1");
+    const int grid = ds->sm_count * 8;
+    uint32_t* out = nullptr;
+    cudaError_t e = cudaMalloc(&out, (size_t)grid * 256 * 4);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {           // first repetition is the warm-up
+        cudaEventRecord(a, 0);
+        e = npk::launch_int_peak(variant, out, iters, grid, 0);
+        cudaEventRecord(b, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    if (e != cudaSuccess) return cuda_fail(e, "int_peak_kernel");
+    const double per_iter = variant == 2 ? 256.0 : 128.0;
+    if (thread_instr_per_s) *thread_instr_per_s = per_iter * iters * (double)grid * 256.0 / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return NPK_OK;
+}
+
+int npk_philox_debug(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    cudaError_t e = npk::launch_philox_debug(ctr, k0, k1, n, out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "philox_debug_kernel launch");
+}
+
+}  // extern "C"

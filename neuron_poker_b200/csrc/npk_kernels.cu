@@ -1,0 +1,708 @@
+// npk_kernels.cu -- hand-written sm_100a kernels for neuron_poker's Monte-Carlo equity hot path.
+//
+//   equity_uniform_kernel<NOPP,NB>  K1  batched (query x trial) Monte-Carlo, uniform dealing
+//                                       replaces MonteCarlo.run_montecarlo's loop (reference montecarlo_python.py:210-239)
+//                                       with the C++ sibling's dealing semantics (Montecarlo.cpp:293-312)
+//   equity_reference_kernel         K1' same loop with the Python reference's own (biased) dealer
+//                                       (montecarlo_python.py:165-189) -- see deal_reference() below
+//   rank7_kernel / rank7_colex      K2  batched 7-card rank ids (hand_evaluator.py:27-119 `_calc_score` ordering)
+//   enum_headsup_kernel             K3  exact heads-up enumeration of opponents and missing board cards
+//   showdown_kernel                 K4  batched get_winner (hand_evaluator.py:9-17)
+//
+// Everything is integer work on 32-bit lanes: no tensor cores, no floating point.  One trial per lane; the rank
+// tables (about 129 KB) are staged once per CTA into shared memory by the bulk-copy engine and gathered with 16-bit
+// LDS; win / tie counts are reduced with warp REDUX and one 64-bit RED per (warp, work item).
+#include "npk_device.cuh"
+#include "npk_kernels.h"
+
+namespace npk {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// work items: (query, chunk of trials).  Warps pull items from a global counter (reset by the host before launch).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long next_item(unsigned long long* counter, int lane)
+{
+    unsigned long long it = 0;
+    if (lane == 0) it = atomicAdd(counter, 1ull);
+    return (long long)__shfl_sync(0xffffffffu, it, 0);
+}
+
+// Per-query constants shared by every trial of a work item.
+struct QueryStatic {
+    uint32_t hero_sum;    // desc(h0) + desc(h1)
+    uint32_t hero_lo, hero_hi;
+    uint32_t board_sum;   // sum of known board descriptors
+    uint32_t board_lo, board_hi;
+    uint32_t board_cnt;   // nibble-per-suit counters of known board cards, each biased by 5 (>= 8 <=> >= 3 cards)
+    uint64_t known;       // bit per card id (rank-major) of hero + known board cards
+};
+
+__device__ __forceinline__ QueryStatic load_query(const EquityParams& p, long long q, int nb_known)
+{
+    QueryStatic s;
+    const uint8_t h0 = p.hole[2 * q], h1 = p.hole[2 * q + 1];
+    uint32_t d0 = p.tables.desc[h0], d1 = p.tables.desc[h1], l, h;
+    s.hero_sum = d0 + d1;
+    card_bits(d0, s.hero_lo, s.hero_hi);
+    card_bits(d1, l, h);
+    s.hero_lo |= l; s.hero_hi |= h;
+    s.known = (1ull << h0) | (1ull << h1);
+    s.board_sum = 0; s.board_lo = 0; s.board_hi = 0; s.board_cnt = 0x5555u;
+    for (int i = 0; i < nb_known; i++) {
+        const uint8_t c = p.board[5 * q + i];
+        uint32_t d = p.tables.desc[c];
+        card_bits(d, l, h);
+        s.board_sum += d; s.board_lo |= l; s.board_hi |= h; s.board_cnt += suit_inc(d);
+        s.known |= 1ull << c;
+    }
+    return s;
+}
+
+// Flush-aware rank id of (board + two hole cards).  `sel`/`thr` describe the only suit that can still flush on this
+// board (the suit holding >= 3 board cards), thr = 5 or 64 (= impossible).
+__device__ __forceinline__ uint32_t eval_player(const SmemTables& s, uint32_t total, uint32_t lo, uint32_t hi,
+                                                uint32_t sel, uint32_t thr)
+{
+    uint32_t v = lookup_nonflush(s, total);
+    uint32_t field = prmt(lo, hi, sel);
+    if ((uint32_t)__popc(field) >= thr) v = max(v, (uint32_t)s.flush[field]);
+    return v;
+}
+
+// =====================================================================================================================
+// K1: uniform dealing.  NOPP opponents, NB board cards still to come (known board = 5 - NB), one trial per lane.
+//
+// Dealing = partial Fisher-Yates over the N = 50 - (5 - NB) unseen cards.  Each warp owns a private copy of the deck in
+// shared memory, interleaved so that lane l only ever touches bank l (element j of lane l at word j*32 + l): every
+// LDS/STS of the shuffle is conflict-free whatever the random indices are.  Elements are the 32-bit card descriptors
+// themselves, so a draw yields everything the evaluator needs with no decode table.  After the D = 2*NOPP + NB draws
+// the D overwritten slots are restored in reverse order from registers, which leaves the deck in its canonical order
+// for the next trial: the outcome of a trial depends only on (seed, query, trial), not on how trials are partitioned.
+//
+// Random numbers: Philox4x32-10, counter = (trial_lo, trial_hi, query, block), key = seed.  Each 32-bit word serves two
+// draws by multiply-shift with remainder reuse: x*m -> (index, x'), x'*(m-1) -> index; bias < 2^-26 per draw.
+// =====================================================================================================================
+template <int NOPP, int NB>
+__global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const EquityParams p)
+{
+    constexpr int KNOWN = 5 - NB;
+    constexpr int N = 50 - KNOWN;          // unseen cards
+    constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
+    constexpr int NW = (D + 1) / 2;        // 32-bit words per trial
+    constexpr int NBLK = (NW + 3) / 4;     // Philox blocks per trial
+    static_assert(D <= N, "not enough cards");
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    const uint32_t table_bytes = 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-warp: 64-word scratch (static deck order) + interleaved deck (52 rows x 32 lanes)
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + 52 * 32);
+    uint32_t* fy = scratch + 64 + lane;
+
+    const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
+    const long long n_items = p.nq * chunks;
+
+    for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
+        const long long qslot = item / chunks, ci = item - qslot * chunks;
+        const long long q = p.qindex ? p.qindex[qslot] : qslot;
+        const QueryStatic qs = load_query(p, q, KNOWN);
+
+        // canonical deck: unseen cards in ascending card id.  Lane l places cards l and l+32.
+        __syncwarp();
+        {
+            const uint64_t avail = ~qs.known & ((1ull << 52) - 1ull);
+            for (int c = lane; c < 52; c += 32)
+                if (avail >> c & 1ull) scratch[__popcll(avail & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < N; j++) fy[j * 32] = scratch[j];
+        __syncwarp();
+
+        const long long t_begin = ci * p.chunk;
+        const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
+        uint32_t wins = 0, ties = 0;
+        unsigned long long wt_pack = 0;   // nine 7-bit win-type counters (<= 64 iterations per item)
+
+        for (long long tb = t_begin; tb < t_end; tb += 32) {
+            const long long t_local = tb + lane;
+            const bool active = t_local < t_end;
+            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
+
+            uint32_t w[NBLK * 4];
+#pragma unroll
+            for (int b = 0; b < NBLK; b++)
+                philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, (uint32_t)b, p.seed_lo, p.seed_hi,
+                              &w[4 * b]);
+
+            uint32_t dv[D > 0 ? D : 1], slot[D > 0 ? D : 1];
+            uint32_t rem = 0;
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                const uint32_t x = (k & 1) ? rem : w[k >> 1];
+                const uint64_t prod = (uint64_t)x * (uint32_t)(N - k);
+                const uint32_t idx = (uint32_t)(prod >> 32);
+                rem = (uint32_t)prod;
+                slot[k] = idx * 32;
+                dv[k] = fy[idx * 32];
+                fy[idx * 32] = fy[(N - 1 - k) * 32];
+            }
+#pragma unroll
+            for (int k = D - 1; k >= 0; k--) fy[slot[k]] = dv[k];
+
+            // board
+            uint32_t bsum = qs.board_sum, blo = qs.board_lo, bhi = qs.board_hi, bcnt = qs.board_cnt;
+#pragma unroll
+            for (int k = 2 * NOPP; k < D; k++) {
+                uint32_t l, h;
+                card_bits(dv[k], l, h);
+                bsum += dv[k]; blo |= l; bhi |= h; bcnt += suit_inc(dv[k]);
+            }
+            const uint32_t f = bcnt & 0x8888u;
+            const uint32_t fs = (31u - __clz(f)) >> 2;
+            const uint32_t sel = 0x9910u + fs * 0x2222u;
+            const uint32_t thr = f ? 5u : 64u;
+
+            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, blo | qs.hero_lo, bhi | qs.hero_hi, sel, thr);
+            uint32_t best = 0;
+#pragma unroll
+            for (int o = 0; o < NOPP; o++) {
+                uint32_t l0, h0, l1, h1;
+                card_bits(dv[2 * o], l0, h0);
+                card_bits(dv[2 * o + 1], l1, h1);
+                const uint32_t ov = eval_player(st, bsum + dv[2 * o] + dv[2 * o + 1], blo | l0 | l1, bhi | h0 | h1, sel, thr);
+                best = max(best, ov);
+            }
+            const bool win = active && hv > best, tie = active && hv == best;
+            wins += win; ties += tie;
+            if (p.win_types && (win || tie)) {
+                uint32_t ty = 0;
+#pragma unroll
+                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                wt_pack += 1ull << (7 * ty);
+            }
+        }
+
+        wins = __reduce_add_sync(0xffffffffu, wins);
+        ties = __reduce_add_sync(0xffffffffu, ties);
+        if (lane == 0) {
+            atomicAdd(&p.wins[q], (unsigned long long)wins);
+            atomicAdd(&p.ties[q], (unsigned long long)ties);
+        }
+        if (p.win_types) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)(wt_pack >> (7 * i)) & 127u);
+                if (lane == 0 && c) atomicAdd(&p.win_types[9 * q + i], (unsigned long long)c);
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
+// K1': the Python reference's dealer (tools/montecarlo_python.py:165-189) on a 52-bit availability mask.
+//   opponent: i1 ~ U[0,n), i2 ~ U[0,n-1), retry while i1 == i2;  c1 = deck.pop(i1); c2 = deck.pop(i2)   (:169-179)
+//             -> c1 = i1-th unseen card in card-id order, c2 = i2-th of the remaining ones
+//   board:    j ~ U[0, n-1)  -> the highest unseen card never reaches the board                            (:188)
+// One Philox word per opponent attempt (i1 from the high product word, i2 from the remainder) and one per board card;
+// words are consumed strictly in order, blocks fetched on demand, so a trial is still a pure function of
+// (seed, query, trial).  Generic in the number of players and known board cards (runtime), one trial per lane.
+// =====================================================================================================================
+struct WordStream {
+    uint32_t c0, c1, c2, k0, k1, blk, have;
+    uint32_t w[4];
+    __device__ __forceinline__ uint32_t next()
+    {
+        if (have == 0) { philox4x32_10(c0, c1, c2, blk++, k0, k1, w); have = 4; }
+        uint32_t r = w[4 - have];
+        have--;
+        return r;
+    }
+};
+
+// k-th (0-based) set bit of a 52-bit mask, by halving on popcounts
+__device__ __forceinline__ int select_bit(uint64_t m, int k)
+{
+    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    int c = __popc(lo), base = 0;
+    uint32_t w = lo;
+    if (k >= c) { k -= c; w = hi; base = 32; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t lowmask = (1u << s) - 1u;
+        const int cl = __popc(w & lowmask);
+        if (k >= cl) { k -= cl; w >>= s; base += s; } else { w &= lowmask; }
+    }
+    return base;
+}
+
+__global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const EquityParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    const int lane = threadIdx.x & 31;
+
+    const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
+    const long long n_items = p.nq * chunks;
+
+    for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
+        const long long qslot = item / chunks, ci = item - qslot * chunks;
+        const long long q = p.qindex ? p.qindex[qslot] : qslot;
+        int known = 0;
+        for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
+        const int nopp = (int)p.n_players[q] - 1;
+        const QueryStatic qs = load_query(p, q, known);
+        const uint64_t avail0 = ~qs.known & ((1ull << 52) - 1ull);
+        const int n0 = __popcll(avail0);
+
+        const long long t_begin = ci * p.chunk;
+        const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
+        uint32_t wins = 0, ties = 0;
+        unsigned long long passes = 0;
+        unsigned long long wt_pack = 0;
+
+        for (long long tb = t_begin; tb < t_end; tb += 32) {
+            const long long t_local = tb + lane;
+            const bool active = t_local < t_end;
+            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
+            WordStream rs;
+            rs.c0 = (uint32_t)trial; rs.c1 = (uint32_t)(trial >> 32); rs.c2 = (uint32_t)q + p.query_offset;
+            rs.k0 = p.seed_lo; rs.k1 = p.seed_hi; rs.blk = 0x80000000u; rs.have = 0;   // stream distinct from K1's
+
+            uint64_t avail = avail0;
+            int n = n0;
+            uint32_t best = 0;
+            uint32_t osum[9], olo[9], ohi[9];
+            if (active) {
+                for (int o = 0; o < nopp; o++) {
+                    uint32_t i1, i2;
+                    do {
+                        const uint64_t prod = (uint64_t)rs.next() * (uint32_t)n;
+                        i1 = (uint32_t)(prod >> 32);
+                        i2 = (uint32_t)(((uint64_t)(uint32_t)prod * (uint32_t)(n - 1)) >> 32);
+                        passes++;
+                    } while (i1 == i2);
+                    const int c1 = select_bit(avail, (int)i1);
+                    avail &= ~(1ull << c1);
+                    const int c2 = select_bit(avail, (int)i2);
+                    avail &= ~(1ull << c2);
+                    n -= 2;
+                    const uint32_t d1 = p.tables.desc[c1], d2 = p.tables.desc[c2];
+                    uint32_t l1, h1, l2, h2;
+                    card_bits(d1, l1, h1);
+                    card_bits(d2, l2, h2);
+                    osum[o] = d1 + d2; olo[o] = l1 | l2; ohi[o] = h1 | h2;
+                }
+            }
+            uint32_t bsum = qs.board_sum, blo = qs.board_lo, bhi = qs.board_hi, bcnt = qs.board_cnt;
+            if (active) {
+                for (int k = known; k < 5; k++) {
+                    const uint32_t j = (uint32_t)(((uint64_t)rs.next() * (uint32_t)(n - 1)) >> 32);
+                    const int c = select_bit(avail, (int)j);
+                    avail &= ~(1ull << c);
+                    n--;
+                    const uint32_t d = p.tables.desc[c];
+                    uint32_t l, h;
+                    card_bits(d, l, h);
+                    bsum += d; blo |= l; bhi |= h; bcnt += suit_inc(d);
+                }
+            }
+            const uint32_t f = bcnt & 0x8888u;
+            const uint32_t fs = (31u - __clz(f)) >> 2;
+            const uint32_t sel = 0x9910u + fs * 0x2222u;
+            const uint32_t thr = f ? 5u : 64u;
+            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, blo | qs.hero_lo, bhi | qs.hero_hi, sel, thr);
+            if (active)
+                for (int o = 0; o < nopp; o++)
+                    best = max(best, eval_player(st, bsum + osum[o], blo | olo[o], bhi | ohi[o], sel, thr));
+            // a lone hero (players == 1) is the best of one hand (reference: index 0 of a one-element list)
+            const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
+            wins += win; ties += tie;
+            if (p.win_types && (win || tie)) {
+                uint32_t ty = 0;
+#pragma unroll
+                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                wt_pack += 1ull << (7 * ty);
+            }
+        }
+        wins = __reduce_add_sync(0xffffffffu, wins);
+        ties = __reduce_add_sync(0xffffffffu, ties);
+        if (lane == 0) {
+            atomicAdd(&p.wins[q], (unsigned long long)wins);
+            atomicAdd(&p.ties[q], (unsigned long long)ties);
+        }
+        if (p.passes) {
+            // 64-bit warp sum in two halves
+            uint32_t plo = __reduce_add_sync(0xffffffffu, (uint32_t)(passes & 0xffffu));
+            uint32_t phi = __reduce_add_sync(0xffffffffu, (uint32_t)(passes >> 16));
+            if (lane == 0) atomicAdd(&p.passes[q], (unsigned long long)plo + ((unsigned long long)phi << 16));
+        }
+        if (p.win_types) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)(wt_pack >> (7 * i)) & 127u);
+                if (lane == 0 && c) atomicAdd(&p.win_types[9 * q + i], (unsigned long long)c);
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
+// K2: rank ids of 7-card hands
+// =====================================================================================================================
+__global__ void __launch_bounds__(kAuxThreads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
+                                                               long long n, uint16_t* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
+    if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t d[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) d[k] = s_desc[cards[7 * i + k]];
+        out[i] = (uint16_t)eval7_desc(st, d);
+    }
+}
+
+// Hands enumerated in colexicographic order: c0 < c1 < ... < c6, index = sum_i C(c_i, i+1).  `first`..`first+count`.
+__device__ __forceinline__ unsigned long long binom(int n, int k)
+{
+    if (k < 0 || k > n) return 0;
+    unsigned long long r = 1;
+    for (int i = 1; i <= k; i++) r = r * (unsigned long long)(n - k + i) / (unsigned long long)i;
+    return r;
+}
+
+__global__ void __launch_bounds__(kAuxThreads, 1) rank7_colex_kernel(const DeviceTables tables, long long first,
+                                                                     long long count, uint16_t* __restrict__ out)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
+    if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long r = (unsigned long long)(first + i);
+        uint32_t d[7];
+        int hi = 51;
+#pragma unroll
+        for (int k = 7; k >= 1; k--) {
+            int c = hi;
+            while (binom(c, k) > r) c--;       // largest c with C(c,k) <= r
+            r -= binom(c, k);
+            d[k - 1] = s_desc[c];
+            hi = c - 1;
+        }
+        out[i] = (uint16_t)eval7_desc(st, d);
+    }
+}
+
+// =====================================================================================================================
+// K3: exact heads-up enumeration.  One CTA per query: every completion of the board x every opponent pair among the
+// unseen cards.  Also ordered pairs of disjoint opponent hands on a complete board (three players, river).
+// Outputs win / tie / lose from the hero's point of view (hero > / == / < best opponent).
+// =====================================================================================================================
+__global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    uint8_t* extra = smem + 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
+    uint32_t* s_deck = reinterpret_cast<uint32_t*>(extra);            // [52] descriptors of unseen cards
+    uint16_t* s_pairval = reinterpret_cast<uint16_t*>(extra + 256);   // [1326] rank of each opponent pair (river)
+    __shared__ unsigned long long s_acc[3];
+
+    for (long long q = blockIdx.x; q < p.nq; q += gridDim.x) {
+        int known = 0;
+        for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
+        const int nopp = (int)p.n_players[q] - 1;
+        // static parts (recomputed per thread; cheap)
+        uint64_t knownmask = (1ull << p.hole[2 * q]) | (1ull << p.hole[2 * q + 1]);
+        uint32_t hd[2] = {p.tables.desc[p.hole[2 * q]], p.tables.desc[p.hole[2 * q + 1]]};
+        uint32_t bd[5];
+        for (int i = 0; i < known; i++) { bd[i] = p.tables.desc[p.board[5 * q + i]]; knownmask |= 1ull << p.board[5 * q + i]; }
+        const uint64_t avail = ~knownmask & ((1ull << 52) - 1ull);
+        const int n = __popcll(avail);
+        __syncthreads();
+        if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
+        for (int c = threadIdx.x; c < 52; c += blockDim.x)
+            if (avail >> c & 1ull) s_deck[__popcll(avail & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        __syncthreads();
+
+        unsigned long long win = 0, tie = 0, lose = 0;
+        const int missing = 5 - known;
+        if (nopp == 1) {
+            // completions: combinations of `missing` cards out of n, by colex index; pairs: (a < b) out of n
+            long long ncomp = 1;
+            for (int i = 0; i < missing; i++) ncomp = ncomp * (n - i) / (i + 1);
+            const long long npairs = (long long)n * (n - 1) / 2;
+            const long long total = ncomp * npairs;
+            for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+                const long long ic = w / npairs;
+                long long ip = w - ic * npairs;
+                // unrank pair (a < b): ip = C(b,2) + a
+                int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)ip)) * 0.5);
+                while ((long long)b * (b - 1) / 2 > ip) b--;
+                while ((long long)(b + 1) * b / 2 <= ip) b++;
+                const int a = (int)(ip - (long long)b * (b - 1) / 2);
+                // unrank completion
+                int comp[5];
+                {
+                    unsigned long long r = (unsigned long long)ic;
+                    int hi = n - 1;
+                    for (int k = missing; k >= 1; k--) {
+                        int c = hi;
+                        while (binom(c, k) > r) c--;
+                        r -= binom(c, k);
+                        comp[k - 1] = c;
+                        hi = c - 1;
+                    }
+                }
+                bool clash = false;
+                for (int k = 0; k < missing; k++) clash |= (comp[k] == a) | (comp[k] == b);
+                if (clash) continue;
+                uint32_t h7[7], o7[7];
+                h7[0] = hd[0]; h7[1] = hd[1]; o7[0] = s_deck[a]; o7[1] = s_deck[b];
+                for (int k = 0; k < known; k++) { h7[2 + k] = bd[k]; o7[2 + k] = bd[k]; }
+                for (int k = 0; k < missing; k++) { h7[2 + known + k] = s_deck[comp[k]]; o7[2 + known + k] = h7[2 + known + k]; }
+                const uint32_t hv = eval7_desc(st, h7), ov = eval7_desc(st, o7);
+                win += hv > ov; tie += hv == ov; lose += hv < ov;
+            }
+        } else if (nopp == 2 && known == 5) {
+            const int npairs = n * (n - 1) / 2;
+            uint32_t h7[7] = {hd[0], hd[1], bd[0], bd[1], bd[2], bd[3], bd[4]};
+            const uint32_t hv = eval7_desc(st, h7);
+            for (int ip = threadIdx.x; ip < npairs; ip += blockDim.x) {
+                int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)ip)) * 0.5);
+                while (b * (b - 1) / 2 > ip) b--;
+                while ((b + 1) * b / 2 <= ip) b++;
+                const int a = ip - b * (b - 1) / 2;
+                uint32_t o7[7] = {s_deck[a], s_deck[b], bd[0], bd[1], bd[2], bd[3], bd[4]};
+                s_pairval[ip] = (uint16_t)eval7_desc(st, o7);
+            }
+            __syncthreads();
+            const long long total = (long long)npairs * npairs;
+            for (long long w = threadIdx.x; w < total; w += blockDim.x) {
+                const int i1 = (int)(w / npairs), i2 = (int)(w - (long long)i1 * npairs);
+                int b1 = (int)((1.0 + sqrt(1.0 + 8.0 * (double)i1)) * 0.5);
+                while (b1 * (b1 - 1) / 2 > i1) b1--;
+                while ((b1 + 1) * b1 / 2 <= i1) b1++;
+                const int a1 = i1 - b1 * (b1 - 1) / 2;
+                int b2 = (int)((1.0 + sqrt(1.0 + 8.0 * (double)i2)) * 0.5);
+                while (b2 * (b2 - 1) / 2 > i2) b2--;
+                while ((b2 + 1) * b2 / 2 <= i2) b2++;
+                const int a2 = i2 - b2 * (b2 - 1) / 2;
+                if (a1 == a2 || a1 == b2 || b1 == a2 || b1 == b2) continue;
+                const uint32_t best = max((uint32_t)s_pairval[i1], (uint32_t)s_pairval[i2]);
+                win += hv > best; tie += hv == best; lose += hv < best;
+            }
+        }
+        // block reduction: warp shuffles then one shared atomic per warp
+        for (int o = 16; o > 0; o >>= 1) {
+            win += __shfl_down_sync(0xffffffffu, win, o);
+            tie += __shfl_down_sync(0xffffffffu, tie, o);
+            lose += __shfl_down_sync(0xffffffffu, lose, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_acc[0], win); atomicAdd(&s_acc[1], tie); atomicAdd(&s_acc[2], lose);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { p.win[q] = s_acc[0]; p.tie[q] = s_acc[1]; p.lose[q] = s_acc[2]; }
+    }
+}
+
+// =====================================================================================================================
+// K4: batched get_winner (hand_evaluator.py:9-17): first index among the best hands + its hand type
+// =====================================================================================================================
+__global__ void __launch_bounds__(kAuxThreads, 1) showdown_kernel(const DeviceTables tables, const uint8_t* __restrict__ holes,
+                                                                  const uint8_t* __restrict__ n_players,
+                                                                  const uint8_t* __restrict__ board, long long n, int maxp,
+                                                                  int32_t* __restrict__ winner, uint8_t* __restrict__ wtype,
+                                                                  uint16_t* __restrict__ ranks)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
+    if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t d[7];
+#pragma unroll
+        for (int k = 0; k < 5; k++) d[2 + k] = s_desc[board[5 * i + k]];
+        int best = -1;
+        uint32_t bv = 0;
+        const int np = n_players[i];
+        for (int pl = 0; pl < np; pl++) {
+            d[0] = s_desc[holes[(i * maxp + pl) * 2]];
+            d[1] = s_desc[holes[(i * maxp + pl) * 2 + 1]];
+            const uint32_t v = eval7_desc(st, d);
+            if (ranks) ranks[i * maxp + pl] = (uint16_t)v;
+            if (best < 0 || v > bv) { best = pl; bv = v; }
+        }
+        winner[i] = best;
+        uint32_t ty = 0;
+#pragma unroll
+        for (int k = 1; k < 9; k++) ty += bv >= tables.type_start[k];
+        wtype[i] = (uint8_t)ty;
+    }
+}
+
+// Philox words for known-answer tests: out[4*i..] = philox(c[4*i..], key)
+__global__ void philox_debug_kernel(const uint32_t* __restrict__ ctr, uint32_t k0, uint32_t k1, int n, uint32_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t o[4];
+        philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1, o);
+        out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+    }
+}
+
+// Integer-issue microbenchmark (roofline denominator): 8 independent dependency chains per thread, 16x unrolled.
+//   variant 0: LOP3 only (alu pipe)   variant 1: IMAD only (fma pipe)   variant 2: one IMAD + one LOP3 per chain step
+// Instructions per thread per outer iteration: 128 (variants 0, 1) or 256 (variant 2), plus ~3 of loop overhead that
+// is NOT counted -- so the reported rate slightly understates the true issue rate.
+template <int V>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* out, int iters, uint32_t b, uint32_t c)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = threadIdx.x * 8u + j + blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (V == 1 || V == 2) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+                if (V == 0 || V == 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(b), "r"(c));
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) x ^= a[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+cudaError_t launch_int_peak(int variant, uint32_t* out, int iters, int grid, cudaStream_t s)
+{
+    switch (variant) {
+        case 0: int_peak_kernel<0><<<grid, 256, 0, s>>>(out, iters, 0x9E3779B9u, 0x7F4A7C15u); break;
+        case 1: int_peak_kernel<1><<<grid, 256, 0, s>>>(out, iters, 0x9E3779B9u, 0x7F4A7C15u); break;
+        case 2: int_peak_kernel<2><<<grid, 256, 0, s>>>(out, iters, 0x9E3779B9u, 0x7F4A7C15u); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------------
+template <int NOPP, int NB>
+static cudaError_t launch_uniform_t(const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+{
+    auto k = equity_uniform_kernel<NOPP, NB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kEquityThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_uniform_nb(int nopp, const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+{
+    switch (nopp) {
+        case 1: return launch_uniform_t<1, NB>(p, grid, smem, s);
+        case 2: return launch_uniform_t<2, NB>(p, grid, smem, s);
+        case 3: return launch_uniform_t<3, NB>(p, grid, smem, s);
+        case 4: return launch_uniform_t<4, NB>(p, grid, smem, s);
+        case 5: return launch_uniform_t<5, NB>(p, grid, smem, s);
+        case 6: return launch_uniform_t<6, NB>(p, grid, smem, s);
+        case 7: return launch_uniform_t<7, NB>(p, grid, smem, s);
+        case 8: return launch_uniform_t<8, NB>(p, grid, smem, s);
+        case 9: return launch_uniform_t<9, NB>(p, grid, smem, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+{
+    switch (nb) {
+        case 0: return launch_uniform_nb<0>(nopp, p, grid, smem, s);
+        case 1: return launch_uniform_nb<1>(nopp, p, grid, smem, s);
+        case 2: return launch_uniform_nb<2>(nopp, p, grid, smem, s);
+        case 3: return launch_uniform_nb<3>(nopp, p, grid, smem, s);
+        case 4: return launch_uniform_nb<4>(nopp, p, grid, smem, s);
+        case 5: return launch_uniform_nb<5>(nopp, p, grid, smem, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t equity_uniform_smem(const DeviceTables& t)
+{
+    return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + (size_t)(kEquityThreads / 32) * (64 + 52 * 32) * 4;
+}
+
+size_t aux_smem(const DeviceTables& t) { return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + 256 + 1326 * 2 + 64; }
+
+cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(p.tables);
+    cudaError_t e = cudaFuncSetAttribute(equity_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    equity_reference_kernel<<<grid, kRefThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(t);
+    cudaError_t e = cudaFuncSetAttribute(rank7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rank7_kernel<<<grid, kAuxThreads, smem, s>>>(t, cards, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(t);
+    cudaError_t e = cudaFuncSetAttribute(rank7_colex_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rank7_colex_kernel<<<grid, kAuxThreads, smem, s>>>(t, first, count, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_enum(const EnumParams& p, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(p.tables);
+    cudaError_t e = cudaFuncSetAttribute(enum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    enum_kernel<<<grid, kAuxThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_showdown(const DeviceTables& t, const uint8_t* holes, const uint8_t* n_players, const uint8_t* board,
+                            long long n, int maxp, int32_t* winner, uint8_t* wtype, uint16_t* ranks, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(t);
+    cudaError_t e = cudaFuncSetAttribute(showdown_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    showdown_kernel<<<grid, kAuxThreads, smem, s>>>(t, holes, n_players, board, n, maxp, winner, wtype, ranks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_philox_debug(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out, cudaStream_t s)
+{
+    philox_debug_kernel<<<(n + 127) / 128, 128, 0, s>>>(ctr, k0, k1, n, out);
+    return cudaGetLastError();
+}
+
+}  // namespace npk

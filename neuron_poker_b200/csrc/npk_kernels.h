@@ -1,0 +1,55 @@
+// npk_kernels.h -- parameter blocks and host-callable launchers of the kernels in npk_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "npk_device.cuh"
+
+namespace npk {
+
+constexpr int kEquityThreads = 384;   // 12 warps per CTA, one CTA per SM (shared memory bound)
+constexpr int kRefThreads = 512;
+constexpr int kAuxThreads = 512;
+
+struct EquityParams {
+    DeviceTables tables;
+    const uint8_t* hole;          // [Q,2] card ids
+    const uint8_t* board;         // [Q,5] card ids, 0xFF = not dealt yet (known cards first)
+    const uint8_t* n_players;     // [Q]
+    const int32_t* qindex;        // [nq] query ids handled by this launch, or null = 0..nq-1
+    long long nq;
+    long long trials;             // trials per query in this launch
+    long long trial_offset;       // first trial number (sharding a query over launches / GPUs)
+    uint32_t query_offset;        // added to the query number in the Philox counter (sharding queries over GPUs)
+    uint32_t seed_lo, seed_hi;
+    uint32_t chunk;               // trials per work item
+    unsigned long long* work_counter;
+    unsigned long long* wins;     // [Q] hero strictly best
+    unsigned long long* ties;     // [Q] hero ties for best
+    unsigned long long* win_types;// [Q,9] or null: hand type of the hero whenever he wins or ties
+    unsigned long long* passes;   // [Q] or null: reference-mode draw attempts (montecarlo_python.py:167)
+};
+
+struct EnumParams {
+    DeviceTables tables;
+    const uint8_t* hole;
+    const uint8_t* board;
+    const uint8_t* n_players;
+    long long nq;
+    unsigned long long* win;
+    unsigned long long* tie;
+    unsigned long long* lose;
+};
+
+size_t equity_uniform_smem(const DeviceTables& t);
+size_t aux_smem(const DeviceTables& t);
+cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, int grid, size_t smem, cudaStream_t s);
+cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s);
+cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
+cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);
+cudaError_t launch_enum(const EnumParams& p, int grid, cudaStream_t s);
+cudaError_t launch_showdown(const DeviceTables& t, const uint8_t* holes, const uint8_t* n_players, const uint8_t* board,
+                            long long n, int maxp, int32_t* winner, uint8_t* wtype, uint16_t* ranks, int grid, cudaStream_t s);
+cudaError_t launch_int_peak(int variant, uint32_t* out, int iters, int grid, cudaStream_t s);
+cudaError_t launch_philox_debug(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out, cudaStream_t s);
+
+}  // namespace npk

@@ -1,0 +1,199 @@
+"""Drop-in equity calculators of the reference, backed by libnpk's sm_100a kernels.
+
+Reference interfaces mirrored here (same names, positional arguments, return types and error behaviour):
+
+  get_equity(player_cards, table_cards, players, runs) -> float
+        tools/montecarlo_python.py:401-406.  Dealing = the Python reference's own dealer (NPK_DEAL_REFERENCE), ties
+        count as wins.  Unlike the reference it always runs all `runs` trials (the reference silently stops after
+        1 s of wall clock, :235-239, :405).
+  montecarlo(my_cards, cards_on_table, number_of_players, iterations) -> float
+        the pybind11 export tools/montecarlo_cpp/pymontecarlo.cpp:21-23 -> Montecarlo.cpp:240-259.  Uniform dealing,
+        a table of fewer than 3 cards is treated as empty (:242-243), ties count as wins.
+  MonteCarlo().run_montecarlo(...)   tools/montecarlo_python.py:191-252 with .equity/.runs/.passes/.winnerCardTypeList
+
+Install into the environment by assigning the attribute the env binds in its constructor (gym_env/env.py:75-81):
+    env.get_equity = neuron_poker_b200.get_equity          # or patch tools.montecarlo_python.get_equity before
+                                                           # HoldemTable() is constructed
+"""
+import ctypes
+import os
+from collections import Counter
+
+import numpy as np
+
+from . import _lib
+from .cards import HAND_TYPES, NO_CARD, encode_query
+
+DEAL_UNIFORM = _lib.NPK_DEAL_UNIFORM
+DEAL_REFERENCE = _lib.NPK_DEAL_REFERENCE
+_DEAL = {"uniform": DEAL_UNIFORM, "reference": DEAL_REFERENCE, DEAL_UNIFORM: DEAL_UNIFORM,
+         DEAL_REFERENCE: DEAL_REFERENCE}
+
+_seed_state = {"rng": None}
+
+
+def seed(value=None):
+    """Fix the stream of per-call Philox seeds.  Without it each call draws its seed from numpy's GLOBAL legacy RNG,
+    the generator the reference itself consumes (montecarlo_python.py:169-170, 188), so np.random.seed(s) -- which is
+    what HoldemTable.reset(seed) does (gym_env/env.py:141-142) -- makes a whole run reproducible, as in the reference."""
+    _seed_state["rng"] = None if value is None else np.random.RandomState(int(value) & 0xFFFFFFFF)
+
+
+def _next_seed():
+    rng = _seed_state["rng"]
+    draw = rng.randint if rng is not None else np.random.randint
+    return (int(draw(0, 1 << 31)) << 31) | int(draw(0, 1 << 31))
+
+
+def _device():
+    return int(os.environ.get("NPK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def _u8(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def equity_counts(player_cards, table_cards, players, runs, deal_mode="uniform", seed_value=None, win_types=False,
+                  passes=False):
+    """One query through the host-buffer C entry point npk_equity_host: returns dict(wins, ties, runs[, win_types,
+    passes]).  `wins` = trials the hero strictly wins, `ties` = trials tied for best."""
+    players = int(players)                      # numpy.int64 from sum(alive) is what the env passes (env.py:262)
+    runs = int(runs)
+    if players < 1:
+        raise IndexError("list index out of range")     # reference: hands[winner] on an empty list
+    if players > 10:
+        raise ValueError("at most 10 players")
+    hole, board = encode_query(player_cards, table_cards)
+    L = _lib.ensure_init(_device())
+    n_players = np.array([players], dtype=np.uint8)
+    out_w = np.zeros(1, dtype=np.uint64)
+    out_t = np.zeros(1, dtype=np.uint64)
+    out_ty = np.zeros(9, dtype=np.uint64) if win_types else None
+    out_p = np.zeros(1, dtype=np.uint64) if passes else None
+    s = _next_seed() if seed_value is None else int(seed_value)
+    _lib.check(L.npk_equity_host(_u8(hole), _u8(board), _u8(n_players), 1, runs, ctypes.c_uint64(s & (2**64 - 1)),
+                                 _DEAL[deal_mode], _u8(out_w), _u8(out_t), _u8(out_ty) if win_types else None,
+                                 _u8(out_p) if passes else None))
+    res = {"wins": int(out_w[0]), "ties": int(out_t[0]), "runs": runs}
+    if win_types:
+        res["win_types"] = [int(x) for x in out_ty]
+    if passes:
+        res["passes"] = int(out_p[0])
+    return res
+
+
+def equity_counts_batch(hole, board, n_players, trials, seed_value=0, deal_mode="uniform", win_types=False,
+                        passes=False):
+    """Host arrays in, host arrays out (numpy, uint8 [Q,2] / [Q,5] with 0xFF padding / [Q]): one blocking call of
+    npk_equity_host = H2D copy of the queries from pinned staging, the kernels, D2H copy of the counters.
+    Returns dict(wins [Q] uint64, ties [Q] uint64[, win_types [Q,9], passes [Q]])."""
+    hole = np.ascontiguousarray(hole, dtype=np.uint8).reshape(-1, 2)
+    board = np.ascontiguousarray(board, dtype=np.uint8).reshape(-1, 5)
+    n_players = np.ascontiguousarray(n_players, dtype=np.uint8).reshape(-1)
+    Q = len(hole)
+    if not (len(board) == Q and len(n_players) == Q):
+        raise ValueError("hole, board and n_players must describe the same number of queries")
+    L = _lib.ensure_init(_device())
+    out = {"wins": np.zeros(Q, dtype=np.uint64), "ties": np.zeros(Q, dtype=np.uint64)}
+    if win_types:
+        out["win_types"] = np.zeros((Q, 9), dtype=np.uint64)
+    if passes:
+        out["passes"] = np.zeros(Q, dtype=np.uint64)
+    _lib.check(L.npk_equity_host(_u8(hole), _u8(board), _u8(n_players), Q, int(trials),
+                                 ctypes.c_uint64(int(seed_value) & (2**64 - 1)), _DEAL[deal_mode], _u8(out["wins"]),
+                                 _u8(out["ties"]), _u8(out["win_types"]) if win_types else None,
+                                 _u8(out["passes"]) if passes else None))
+    return out
+
+
+def get_equity(player_cards, table_cards, players, runs):
+    """Get equity from a montecarlo run -- drop-in for tools/montecarlo_python.py:401-406 (reference dealing)."""
+    r = equity_counts(player_cards, table_cards, players, runs, deal_mode="reference")
+    return (r["wins"] + r["ties"]) / runs
+
+
+def montecarlo(my_cards, cards_on_table, number_of_players, iterations):
+    """Drop-in for the C++ calculator pymontecarlo.montecarlo (Montecarlo.cpp:240-259): uniform dealing; a table with
+    fewer than 3 cards (the reference's callers pass {'null'}) is cleared (:242-243)."""
+    table = list(cards_on_table)
+    if len(table) < 3:
+        table = []
+    try:
+        r = equity_counts(my_cards, table, number_of_players, iterations, deal_mode="uniform")
+    except ValueError as exc:                   # pybind11 surfaces std::runtime_error as RuntimeError
+        raise RuntimeError("Card Type error!") from exc
+    return (r["wins"] + r["ties"]) / iterations
+
+
+class MonteCarlo(object):
+    """Mirror of tools/montecarlo_python.py::MonteCarlo for the path get_equity uses (opponent_range=1, no ghost cards)."""
+
+    def create_card_deck(self):
+        from .cards import DECK
+        return list(DECK)
+
+    def run_montecarlo(self, original_player_card_list, original_table_card_list, player_amount, ui, maxRuns,
+                       timeout, ghost_cards, opponent_range=1):
+        """montecarlo_python.py:191-252.  `ui` and `timeout` are accepted and ignored (every run is executed)."""
+        if ghost_cards != '' or isinstance(opponent_range, set) or float(opponent_range) != 1.0:
+            raise NotImplementedError("opponent ranges / ghost cards are outside this path (SURVEY 8f-2)")
+        if len(original_player_card_list) != 1 or isinstance(original_player_card_list[0], set):
+            raise NotImplementedError("exactly one known hand (the hero) is supported")
+        r = equity_counts(original_player_card_list[0], original_table_card_list, player_amount, maxRuns,
+                          deal_mode="reference", win_types=True, passes=True)
+        runs = r["runs"]
+        self.equity = (r["wins"] + r["ties"]) / runs
+        self.winnerCardTypeList = Counter({HAND_TYPES[i]: c / runs for i, c in enumerate(r["win_types"]) if c})
+        self.winTypesDict = self.winnerCardTypeList.items()
+        self.runs = runs
+        self.passes = r["passes"]
+        return self.equity, self.winTypesDict
+
+
+# ---- batched API on device tensors -----------------------------------------------------------------------------------
+def _as_cuda_u8(x, device, shape_tail):
+    import torch
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.uint8))
+    if x.dtype != torch.uint8:
+        x = x.to(torch.uint8)
+    x = x.to(device, non_blocking=True).contiguous()
+    assert tuple(x.shape[1:]) == tuple(shape_tail), (x.shape, shape_tail)
+    return x
+
+
+def get_equity_batch(hole, board, n_players, trials, seed_value=0, deal_mode="uniform", trial_offset=0, device=None,
+                     uniform_shape=None, validate=True, win_types=False, passes=False, out=None, query_offset=0):
+    """Monte-Carlo counts for a batch of queries on the GPU (asynchronous on the current torch stream).
+
+    hole [Q,2], board [Q,5] (0xFF padding), n_players [Q]: uint8 torch tensors (or array-likes, copied to the device).
+    uniform_shape=(players, known_board_cards) promises every query has that shape (no classification round trip).
+    trial_offset / query_offset shift the Philox counters, so shards of a larger job reproduce its exact numbers.
+    Returns dict of int64 CUDA tensors: wins [Q], ties [Q] (+ win_types [Q,9], passes [Q]); the counters are u64 on
+    the device and viewed as int64.  `out` may hold preallocated zeroed tensors to accumulate into.
+    """
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    hole = _as_cuda_u8(hole, dev, (2,))
+    board = _as_cuda_u8(board, dev, (5,))
+    n_players = _as_cuda_u8(n_players, dev, ())
+    Q = hole.shape[0]
+    L = _lib.ensure_init(dev.index if dev.index is not None else 0)
+    with torch.cuda.device(dev):
+        out = {} if out is None else out
+        for name, shape, want in (("wins", (Q,), True), ("ties", (Q,), True), ("win_types", (Q, 9), win_types),
+                                  ("passes", (Q,), passes)):
+            if want and name not in out:
+                out[name] = torch.zeros(shape, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(L.npk_equity_workspace_bytes(Q)), dtype=torch.uint8, device=dev)
+        up, uk = (-1, -1) if uniform_shape is None else (int(uniform_shape[0]), int(uniform_shape[1]))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.npk_equity_batch(hole.data_ptr(), board.data_ptr(), n_players.data_ptr(), Q, int(trials), up, uk,
+                                      ctypes.c_uint64(int(seed_value) & (2**64 - 1)), int(trial_offset),
+                                      int(query_offset), _DEAL[deal_mode], _lib.NPK_FLAG_VALIDATE if validate else 0,
+                                      out["wins"].data_ptr(), out["ties"].data_ptr(),
+                                      out["win_types"].data_ptr() if win_types else None,
+                                      out["passes"].data_ptr() if passes else None, ws.data_ptr(), stream))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    out["trials"] = int(trials)
+    return out

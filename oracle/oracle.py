@@ -105,10 +105,21 @@ def class_tuples():
     return out
 
 
+def rank_of_tuple(score, ranks):
+    """rank id of a (score, card_ranks) tuple"""
+    return class_tuples().index((tuple(score), tuple(ranks)))
+
+
 def rank7(cards):
     a = ids(cards)
     assert len(a) == 7
     return lib().oracle_rank7(_p(a))
+
+
+def type7(cards):
+    """hand type index 0..8 of a 7-card hand (position in CAT_NAMES)"""
+    a = ids(cards)
+    return lib().oracle_type7(_p(a))
 
 
 def rank7_batch(cards):

@@ -1,0 +1,107 @@
+"""Executable specification of libnpk's two samplers, in plain Python (test infrastructure).
+
+The GPU kernels deal cards from a Philox4x32-10 stream keyed by (seed; trial, query).  This module restates that
+procedure card for card, and scores the resulting hands with the ORACLE evaluator (oracle/), so a GPU run can be
+checked for bit-identical win / tie / pass / win-type counts -- not only statistically.
+
+  uniform   (npk_kernels.cu equity_uniform_kernel): partial Fisher-Yates over the unseen cards in ascending card id;
+            draw k takes index hi32(x * (N-k)) where x is a fresh Philox word for even k and the low product word of
+            the previous draw for odd k; the hole left by a draw is filled with the last live element.
+  reference (equity_reference_kernel): the Python reference's dealer, montecarlo_python.py:165-189, on the ordered
+            list of unseen cards: one word per opponent attempt (i1 = hi32(w*n), i2 = hi32(lo32(w*n)*(n-1)), retry while
+            i1 == i2, pop(i1) then pop(i2)), one word per board card (j = hi32(w*(n-1)), never the last card).
+"""
+M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+MASK = 0xFFFFFFFF
+REFERENCE_BLOCK0 = 0x80000000
+
+
+def philox4x32_10(ctr, key):
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return [c0, c1, c2, c3]
+
+
+def deal_uniform(seed, query, trial, hole, board, players):
+    """Returns (opponent hands [[c1,c2],...], full board [5])."""
+    known = set(hole) | set(board)
+    deck = [c for c in range(52) if c not in known]
+    n = len(deck)
+    nopp = players - 1
+    d = 2 * nopp + (5 - len(board))
+    nblk = ((d + 1) // 2 + 3) // 4
+    key = (seed & MASK, (seed >> 32) & MASK)
+    w = []
+    for b in range(nblk):
+        w += philox4x32_10((trial & MASK, (trial >> 32) & MASK, query & MASK, b), key)
+    out, rem = [], 0
+    for k in range(d):
+        x = rem if k & 1 else w[k >> 1]
+        prod = x * (n - k)
+        idx, rem = prod >> 32, prod & MASK
+        out.append(deck[idx])
+        deck[idx] = deck[n - 1 - k]
+    opp = [out[2 * i:2 * i + 2] for i in range(nopp)]
+    return opp, list(board) + out[2 * nopp:]
+
+
+class _Words:
+    def __init__(self, seed, query, trial):
+        self.key = (seed & MASK, (seed >> 32) & MASK)
+        self.ctr = (trial & MASK, (trial >> 32) & MASK, query & MASK)
+        self.blk, self.buf = REFERENCE_BLOCK0, []
+
+    def next(self):
+        if not self.buf:
+            self.buf = philox4x32_10(self.ctr + (self.blk & MASK,), self.key)
+            self.blk += 1
+        return self.buf.pop(0)
+
+
+def deal_reference(seed, query, trial, hole, board, players):
+    """Returns (opponent hands, full board, passes)."""
+    known = set(hole) | set(board)
+    deck = [c for c in range(52) if c not in known]
+    ws = _Words(seed, query, trial)
+    opp, passes = [], 0
+    for _ in range(players - 1):
+        n = len(deck)
+        while True:
+            passes += 1
+            prod = ws.next() * n
+            i1, i2 = prod >> 32, ((prod & MASK) * (n - 1)) >> 32
+            if i1 != i2:
+                break
+        c1 = deck.pop(i1)
+        c2 = deck.pop(i2)
+        opp.append([c1, c2])
+    full = list(board)
+    while len(full) < 5:
+        j = (ws.next() * (len(deck) - 1)) >> 32
+        full.append(deck.pop(j))
+    return opp, full, passes
+
+
+def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_offset=0):
+    """dict(wins, ties, passes, win_types[9]) of the modelled sampler scored by the oracle's rank ids."""
+    wins = ties = passes = 0
+    types = [0] * 9
+    for t in range(trial_offset, trial_offset + trials):
+        if mode == "uniform":
+            opp, full = deal_uniform(seed, query, t, hole, board, players)
+        else:
+            opp, full, p = deal_reference(seed, query, t, hole, board, players)
+            passes += p
+        hv = oracle.rank7(list(hole) + full)
+        best = max([oracle.rank7(o + full) for o in opp], default=-1)
+        if hv > best:
+            wins += 1
+        elif hv == best:
+            ties += 1
+        if hv >= best:
+            types[oracle.type7(list(hole) + full)] += 1
+    return {"wins": wins, "ties": ties, "passes": passes, "win_types": types}

@@ -1,0 +1,341 @@
+"""GPU parity tests: libnpk's CUDA kernels, called through the C ABI, against the oracle and the golden fixtures.
+
+Bar: bit-exact for rank ids, showdown winners, enumerated (win, tie, lose) counts AND for Monte-Carlo counts against
+the executable sampler specification (tests/sampler_model.py scored by the oracle); statistical (3 sigma of the binomial
+standard error, as BASELINE.json's north_star states) only where two different random streams are compared.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+import neuron_poker_b200 as npk
+import oracle
+import sampler_model
+from neuron_poker_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+NO = 0xFF
+
+
+def ids(cards):
+    return [npk.card_id(c) for c in cards]
+
+
+def pad_board(b):
+    return list(b) + [NO] * (5 - len(b))
+
+
+def sigma(p, n):
+    return math.sqrt(max(p * (1 - p), 1e-12) / n)
+
+
+@pytest.fixture(scope="module")
+def torch_mod(cuda_device):
+    import torch
+    _lib.ensure_init(0)
+    return torch
+
+
+def test_philox_known_answers(torch_mod):
+    torch = torch_mod
+    ctrs = [(0, 0, 0, 0), (0xffffffff,) * 4, (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (5, 0, 77, 1)]
+    keys = [(0, 0), (0xffffffff, 0xffffffff), (0xa4093822, 0x299f31d0), (123, 456)]
+    for c, k in zip(ctrs, keys):
+        ctr = torch.tensor(np.array(c, dtype=np.uint32).view(np.int32), device="cuda")
+        out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().npk_philox_debug(ctr.data_ptr(), k[0], k[1], 1, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().view(np.uint32).tolist()
+        assert got == sampler_model.philox4x32_10(c, k)
+    assert sampler_model.philox4x32_10((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_rank7_golden_and_oracle(torch_mod, golden_cases, golden_tables):
+    hands = golden_cases["random_hands"] + golden_cases["rare_hands"]
+    cards = np.array([h["cards"] for h in hands], dtype=np.uint8)
+    got = npk.rank7(cards).cpu().numpy()
+    assert (got == np.array([h["rank_id"] for h in hands])).all()
+    rng = np.random.default_rng(3)
+    big = np.stack([rng.permutation(52)[:7] for _ in range(200000)]).astype(np.uint8)
+    assert (npk.rank7(big).cpu().numpy() == oracle.rank7_batch(big)).all()
+    # every rank histogram (non-flush suits) and every flush mask: the whole key space of the evaluator
+    hist = golden_tables["hist"]
+    hc = np.zeros((len(hist), 7), dtype=np.uint8)
+    for i, h in enumerate(hist):
+        k = 0
+        for r in range(13):
+            for _ in range(h[r]):
+                hc[i, k] = 4 * r + (k & 3)
+                k += 1
+    assert (npk.rank7(hc).cpu().numpy() == golden_tables["nonflush"]).all()
+    fl = golden_tables["flush"]
+    masks = [m for m in range(8192) if fl[m] != 0xFFFF]
+    for suit in range(4):
+        fc = []
+        for m in masks:
+            c = [4 * r + suit for r in range(13) if m >> r & 1]
+            pad = 0
+            while len(c) < 7:
+                c.append(4 * pad + (suit + 1) % 4)
+                pad += 1
+            fc.append(c)
+        assert (npk.rank7(np.array(fc, dtype=np.uint8)).cpu().numpy() == fl[masks]).all()
+
+
+def test_rank7_empty_and_ragged(torch_mod):
+    torch = torch_mod
+    assert npk.rank7(np.zeros((0, 7), dtype=np.uint8)).numel() == 0
+    one = npk.rank7(np.array([[0, 4, 8, 12, 16, 21, 25]], dtype=np.uint8)).cpu().numpy()   # 2C 3C 4C 5C 6C 7D 8D
+    assert one[0] == oracle.rank7([0, 4, 8, 12, 16, 21, 25])
+
+
+def test_known_answer_showdowns(torch_mod, golden_cases):
+    for case in golden_cases["known"]:
+        if case["name"] in ("3", "6b"):
+            continue        # duplicate physical cards: expressible only at table level, see test below
+        best, ty = npk.eval_best_hand(case["hands"])
+        assert best == case["hands"][case["winner"]] and ty == case["winner_type"], case["name"]
+
+
+def test_duplicate_card_cases_at_table_level(golden_cases):
+    """Cases 3 and 6b of tests/test_evaluator.py hold duplicate cards; their values are still (histogram, flush mask)
+    keys of the lookup tables, which is what is compared here (host copy of the device tables)."""
+    t = npk.host_tables()
+    for case in golden_cases["known"]:
+        if case["name"] not in ("3", "6b"):
+            continue
+        vals = []
+        for hand in case["hands"]:
+            cid = ids(hand)
+            suits = [c & 3 for c in cid]
+            fs = [s for s in range(4) if suits.count(s) >= 5]
+            if fs:
+                mask = 0
+                for c in cid:
+                    if (c & 3) == fs[0]:
+                        mask |= 1 << (c >> 2)
+                if bin(mask).count("1") >= 5:
+                    vals.append(int(t["flush"][mask]))
+                    continue
+            mk = sum(int(t["desc"][4 * (c >> 2)]) >> 9 for c in cid) & ((1 << 23) - 1)
+            vals.append(int(t["value"][int(t["rowoff"][mk >> 10]) + (mk & 1023)]))
+        exp = [oracle.rank_of_tuple(tuple(tp[0]), tuple(tp[1])) for tp in case["tuples"]]
+        if case["name"] == "3":
+            assert vals == exp
+        assert vals.index(max(vals)) == case["winner"]
+
+
+def test_showdown_batch(torch_mod, golden_cases):
+    sds = golden_cases["showdowns"]
+    maxp = 9
+    holes = np.zeros((len(sds), maxp, 2), dtype=np.uint8)
+    npl = np.zeros(len(sds), dtype=np.uint8)
+    board = np.zeros((len(sds), 5), dtype=np.uint8)
+    for i, s in enumerate(sds):
+        npl[i] = len(s["holes"])
+        holes[i, :npl[i]] = s["holes"]
+        holes[i, npl[i]:] = [[0, 1]] * (maxp - npl[i])
+        board[i] = s["board"]
+    w, t, r = npk.showdown(holes, npl, board, return_ranks=True)
+    assert (w.cpu().numpy() == np.array([s["winner"] for s in sds])).all()
+    assert (t.cpu().numpy() == np.array([s["type"] for s in sds])).all()
+    s0 = sds[0]
+    assert npk.get_winner([[npk.card_str(c) for c in h] for h in s0["holes"]],
+                          [npk.card_str(c) for c in s0["board"]])[0] == s0["winner"]
+    rk = r.cpu().numpy()
+    for i in range(0, len(sds), 50):
+        for p in range(npl[i]):
+            assert rk[i, p] == oracle.rank7(list(sds[i]["holes"][p]) + list(sds[i]["board"]))
+
+
+def test_enumeration_bit_exact(torch_mod, golden_enum):
+    spots = [s for s in golden_enum["spots"] if "uniform" in s]
+    hole = np.array([ids(s["hero"]) for s in spots], dtype=np.uint8)
+    board = np.array([pad_board(ids(s["board"])) for s in spots], dtype=np.uint8)
+    npl = np.array([s["players"] for s in spots], dtype=np.uint8)
+    w, t, l = npk.enumerate_equity(hole, board, npl)
+    got = np.stack([w.cpu().numpy(), t.cpu().numpy(), l.cpu().numpy()], 1).tolist()
+    for s, g in zip(spots, got):
+        assert g == s["uniform"], (s["name"], g)
+    rnd = golden_enum["random_spots"]
+    hole = np.array([ids(s["hero"]) for s in rnd], dtype=np.uint8)
+    board = np.array([pad_board(ids(s["board"])) for s in rnd], dtype=np.uint8)
+    w, t, l = npk.enumerate_equity(hole, board)
+    got = np.stack([w.cpu().numpy(), t.cpu().numpy(), l.cpu().numpy()], 1).tolist()
+    assert got == [s["uniform"] for s in rnd]
+
+
+def test_enumeration_synthetic_batch_vs_oracle(torch_mod):
+    """cfg 2: seeded random heads-up river and turn spots, GPU counts == CPU enumeration with the oracle evaluator."""
+    rng = np.random.default_rng(0)
+    hole, board = [], []
+    for i in range(192):
+        nb = 5 if i % 2 == 0 else 4
+        c = rng.permutation(52)[:2 + nb].tolist()
+        hole.append(c[:2])
+        board.append(pad_board(c[2:]))
+    w, t, l = npk.enumerate_equity(np.array(hole, dtype=np.uint8), np.array(board, dtype=np.uint8))
+    w, t, l = w.cpu().numpy(), t.cpu().numpy(), l.cpu().numpy()
+    for i in range(192):
+        b = [c for c in board[i] if c != NO]
+        assert (int(w[i]), int(t[i]), int(l[i])) == oracle.enum_headsup(hole[i], b)
+        assert w[i] + t[i] + l[i] == (990 if len(b) == 5 else 45540)
+
+
+def _run_batch(torch, hole, board, npl, trials, seed, mode, **kw):
+    out = npk.get_equity_batch(np.array(hole, dtype=np.uint8), np.array(board, dtype=np.uint8),
+                               np.array(npl, dtype=np.uint8), trials, seed_value=seed, deal_mode=mode, **kw)
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+
+
+MODEL_QUERIES = [
+    (["AS", "KS"], [], 2), (["AS", "KS"], [], 3), (["8S", "TS"], [], 5), (["7D", "7C"], [], 10),
+    (["3S", "QH"], ["2C", "5H", "7C"], 2), (["AS", "KS"], ["2C", "7D", "KH"], 6), (["TC", "TH"], ["4D", "QD", "KC"], 9),
+    (["5H", "KD"], ["KH", "JS", "2C", "QS"], 2), (["5H", "KD"], ["KH", "JS", "2C", "QS"], 4),
+    (["3H", "3S"], ["8S", "4S", "QH", "8C", "4H"], 2), (["JD", "JS"], ["8C", "TC", "JC", "5H", "QC"], 3),
+    (["8S", "2S"], ["5S", "3S", "4S", "KS", "AS"], 7), (["2H", "2D"], ["2C"], 3), (["9H", "9D"], ["2C", "3D"], 4),
+    (["AH", "KH"], ["QH", "JH", "2C"], 6), (["AS", "AD"], [], 1),
+]
+
+
+@pytest.mark.parametrize("mode", ["uniform", "reference"])
+def test_montecarlo_counts_equal_sampler_specification(torch_mod, mode):
+    """Mixed-shape batch: wins / ties / win types (/ passes) bit-identical to the Python specification + oracle."""
+    torch = torch_mod
+    hole = [ids(q[0]) for q in MODEL_QUERIES]
+    board = [pad_board(ids(q[1])) for q in MODEL_QUERIES]
+    npl = [q[2] for q in MODEL_QUERIES]
+    trials, seed = 150, 0x1234567890ABCDEF
+    out = _run_batch(torch, hole, board, npl, trials, seed, mode, win_types=True, passes=(mode == "reference"))
+    for qi, (h, b, p) in enumerate(MODEL_QUERIES):
+        m = sampler_model.run_model(oracle, mode, seed, qi, ids(h), ids(b), p, trials)
+        assert (int(out["wins"][qi]), int(out["ties"][qi])) == (m["wins"], m["ties"]), (mode, qi)
+        assert out["win_types"][qi].tolist() == m["win_types"], (mode, qi)
+        if mode == "reference":
+            assert int(out["passes"][qi]) == m["passes"], qi
+
+
+def test_partition_invariance(torch_mod):
+    """Counts depend only on (seed, query, trial): splitting the trials over calls (trial_offset) or running a query
+    alone gives bit-identical totals.  This is what makes multi-GPU sharding exact."""
+    torch = torch_mod
+    hole = [ids(["AS", "KS"]), ids(["7D", "7C"])]
+    board = [pad_board(ids(["2C", "7D", "KH"])), pad_board(ids(["2C", "7S", "KH"]))]
+    npl = [6, 6]
+    for mode in ("uniform", "reference"):
+        whole = _run_batch(torch, hole, board, npl, 5000, 99, mode, uniform_shape=(6, 3))
+        acc_w = np.zeros(2, dtype=np.int64)
+        acc_t = np.zeros(2, dtype=np.int64)
+        for off, n in ((0, 1777), (1777, 1200), (2977, 2023)):
+            part = _run_batch(torch, hole, board, npl, n, 99, mode, trial_offset=off, uniform_shape=(6, 3))
+            acc_w += part["wins"]
+            acc_t += part["ties"]
+        assert (acc_w == whole["wins"]).all() and (acc_t == whole["ties"]).all(), mode
+        mixed = _run_batch(torch, hole, board, npl, 5000, 99, mode)           # classified path, same numbers
+        assert (mixed["wins"] == whole["wins"]).all() and (mixed["ties"] == whole["ties"]).all()
+
+
+def test_uniform_mode_matches_exact_enumeration(torch_mod, golden_enum):
+    """UNIFORM dealing vs exact combinatorics, 3 sigma at 1M trials."""
+    torch = torch_mod
+    spots = [s for s in golden_enum["spots"] if "uniform" in s]
+    hole = [ids(s["hero"]) for s in spots]
+    board = [pad_board(ids(s["board"])) for s in spots]
+    npl = [s["players"] for s in spots]
+    trials = 1000000
+    out = _run_batch(torch, hole, board, npl, trials, 2026, "uniform")
+    for i, s in enumerate(spots):
+        w, t, l = s["uniform"]
+        tot = w + t + l
+        for got, exact in ((out["wins"][i], w / tot), (out["ties"][i], t / tot)):
+            assert abs(got / trials - exact) <= 3 * sigma(exact, trials) + 1e-9, (s["name"], got / trials, exact)
+
+
+def test_reference_mode_matches_reference_dealer_expectation(torch_mod, golden_enum):
+    """REFERENCE dealing vs the exact expectation of the reference's own dealer (weighted enumeration)."""
+    torch = torch_mod
+    spots = [s for s in golden_enum["spots"] if "reference_mode" in s]
+    hole = [ids(s["hero"]) for s in spots]
+    board = [pad_board(ids(s["board"])) for s in spots]
+    trials = 1000000
+    out = _run_batch(torch, hole, board, [2] * len(spots), trials, 7, "reference")
+    for i, s in enumerate(spots):
+        num, den = s["reference_mode"]
+        p = num / den
+        got = (out["wins"][i] + out["ties"][i]) / trials
+        assert abs(got - p) <= 3 * sigma(p, trials) + 1e-9, (s["name"], got, p)
+
+
+def test_reference_mode_within_3_sigma_of_reference_runs(torch_mod, golden_mc):
+    """Sampled equities vs the reference's own seeded runs (mc_seeded.json): |p_gpu - p_ref| <= 3 sigma of the
+    reference's binomial standard error at ITS trial count (the GPU runs 400k trials, so its own error is negligible)."""
+    torch = torch_mod
+    by_name = {}
+    for r in golden_mc["runs"]:
+        e = by_name.setdefault(r["name"], {"hero": r["hero"], "board": r["board"], "players": r["players"], "w": 0, "n": 0})
+        e["w"] += r["wins"]
+        e["n"] += r["runs"]
+    names = sorted(by_name)
+    hole = [ids(by_name[n]["hero"]) for n in names]
+    board = [pad_board(ids(by_name[n]["board"])) for n in names]
+    npl = [by_name[n]["players"] for n in names]
+    trials = 400000
+    out = _run_batch(torch, hole, board, npl, trials, 31337, "reference")
+    for i, n in enumerate(names):
+        e = by_name[n]
+        p_ref = e["w"] / e["n"]
+        p_gpu = (out["wins"][i] + out["ties"][i]) / trials
+        assert abs(p_gpu - p_ref) <= 3 * math.sqrt(sigma(p_gpu, e["n"]) ** 2 + sigma(p_gpu, trials) ** 2), (n, p_gpu, p_ref)
+
+
+def test_dropin_api(torch_mod):
+    """get_equity / montecarlo / MonteCarlo mirror the reference's signatures, types and argument handling."""
+    npk.seed(5)
+    eq = npk.get_equity({"AS", "KS"}, set(), np.int64(2), 20000)          # env passes sets and numpy.int64 (env.py:261-262)
+    assert isinstance(eq, float) and abs(eq - 0.6608) < 0.015             # reference dealer: 0.661
+    eq = npk.montecarlo({"AS", "KS"}, {"null"}, 2, 20000)                  # C++ call site convention for "no board"
+    assert isinstance(eq, float) and abs(eq - 0.6795) < 0.015             # uniform dealing: 0.679
+    assert npk.get_equity(["8S", "2S"], ["5S", "3S", "4S", "KS", "AS"], 2, 2000) == 1.0     # test_montecarlo7
+    assert npk.get_equity({"AS", "KS"}, set(), 1, 500) == 1.0             # players == 1 -> 1.0
+    mc = npk.MonteCarlo()
+    equity, win_types = mc.run_montecarlo([["3H", "3S"]], ["8S", "4S", "QH", "8C", "4H"], 2, 1, maxRuns=15000,
+                                          timeout=0, ghost_cards="", opponent_range=1)
+    assert abs(equity * 100 - 40.2) < 3                                    # tests/test_montecarlo_python.py:44-50, :40
+    assert abs(sum(mc.winnerCardTypeList.values()) - equity) < 1e-4       # :32
+    assert mc.runs == 15000 and mc.passes >= 15000 and dict(win_types) == dict(mc.winnerCardTypeList)
+    with pytest.raises(ValueError):
+        npk.get_equity({"AS", "XX"}, set(), 2, 10)
+    npk.seed(5)
+    a = npk.get_equity({"AS", "KS"}, set(), 2, 3000)
+    npk.seed(5)
+    assert npk.get_equity({"AS", "KS"}, set(), 2, 3000) == a              # reproducible under a fixed seed
+    np.random.seed(11); npk.seed(None)
+    b = npk.get_equity({"AS", "KS"}, set(), 2, 3000)
+    np.random.seed(11)
+    assert npk.get_equity({"AS", "KS"}, set(), 2, 3000) == b              # np.random.seed governs it like the reference
+
+
+def test_reference_montecarlo_test_spots(torch_mod, golden_enum):
+    """The reference's own 19 non-range Monte-Carlo spots with its own acceptance rule:
+    |mean of 5 runs - expected| < 3 points and stdev < 3 (tests/test_montecarlo_python.py:15-41)."""
+    npk.seed(1)
+    for s in golden_enum["spots"]:
+        res = [100 * npk.get_equity(s["hero"], s["board"], s["players"], 15000) for _ in range(5)]
+        assert abs(np.mean(res) - s["test_expected_pct"]) < 3 and np.std(res) < 3, (s["name"], res)
+
+
+def test_invalid_queries_are_reported(torch_mod):
+    torch = torch_mod
+    with pytest.raises(_lib.NpkError) as e:
+        _run_batch(torch, [[51, 51]], [pad_board([])], [2], 10, 0, "uniform")
+    assert e.value.code == -5
+    with pytest.raises(_lib.NpkError):
+        _run_batch(torch, [[0, 1]], [[2, NO, 3, NO, NO]], [2], 10, 0, "uniform")
+    with pytest.raises(_lib.NpkError):
+        _run_batch(torch, [[0, 1]], [pad_board([])], [11], 10, 0, "reference")
+    out = _run_batch(torch, np.zeros((0, 2)), np.zeros((0, 5)), np.zeros((0,)), 10, 0, "uniform")
+    assert out["wins"].shape == (0,)

@@ -1,0 +1,123 @@
+"""CPU-side checks of the product: libnpk.so loads and exports the whole C ABI, the host-built lookup tables equal the
+golden tables generated from the reference, the Python boundary mirrors the reference's argument handling, and every
+compute entry point fails loudly when no GPU is present (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import neuron_poker_b200 as npk
+from neuron_poker_b200 import _lib, cards
+import sampler_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_every_declared_symbol_is_exported():
+    header = open(os.path.join(ROOT, "include", "npk.h")).read()
+    names = set(re.findall(r"\b(npk_[a-z0-9_]+)\s*\(", header))
+    assert {"npk_init", "npk_equity_batch", "npk_equity_host", "npk_rank7_batch", "npk_enum_batch",
+            "npk_showdown_batch", "npk_rank7_colex"} <= names
+    L = _lib.lib()
+    for n in sorted(names):
+        assert hasattr(L, n), n
+
+
+def test_host_tables_equal_reference_tables(golden_tables):
+    t = npk.host_tables()
+    assert list(t["type_start"]) == [0, 407, 1877, 2640, 3215, 3225, 4502, 4658, 4736, 5034]
+    gold_flush = golden_tables["flush"]
+    valid = gold_flush != 0xFFFF
+    assert (t["flush"][valid] == gold_flush[valid]).all()
+    # every rank histogram through descriptor sums + row displacement (same arithmetic as the device code)
+    hist = golden_tables["hist"].astype(np.uint32)
+    desc_key = (t["desc"][::4] >> 9).astype(np.uint64)                 # mixed rank key of each rank (suit C cards)
+    mk = (hist.astype(np.uint64) * desc_key[None, :]).sum(1) & ((1 << 23) - 1)
+    ids = t["value"][t["rowoff"][(mk >> 10).astype(np.int64)].astype(np.int64) + (mk & 1023).astype(np.int64)]
+    assert (ids == golden_tables["nonflush"]).all()
+    assert len(t["value"]) * 2 + 2 * 8192 * 2 < 140 * 1024              # fits one CTA's shared memory with room for decks
+    # class keys: type in the high word, same census as the reference
+    types = (t["class_keys"] >> np.uint64(32)).astype(int)
+    assert np.bincount(types, minlength=9).tolist() == [407, 1470, 763, 575, 10, 1277, 156, 78, 298]
+    enc = golden_tables["classes"]
+    assert (types == enc[:, 0]).all()
+    for i in range(0, 5034, 7):
+        ranks = [int(r) for r in enc[i, 1:] if r != -2]
+        key = int(t["class_keys"][i]) & 0xFFFFFFFF
+        got = [((key >> (4 * (7 - j))) & 15) - 2 for j in range(8) if (key >> (4 * (7 - j))) & 15]
+        assert got == ranks, i
+
+
+def test_host_rank7_against_golden_hands(golden_cases):
+    hands = golden_cases["random_hands"] + golden_cases["rare_hands"]
+    c = np.array([h["cards"] for h in hands], dtype=np.uint8)
+    assert (npk.host_rank7(c) == np.array([h["rank_id"] for h in hands])).all()
+
+
+def test_card_notation_and_errors():
+    assert cards.DECK[:5] == ["2C", "2D", "2H", "2S", "3C"] and cards.DECK[-1] == "AS"     # montecarlo_python.py:114-119
+    assert npk.card_id("AS") == 51 and npk.card_str(0) == "2C"
+    hole, board = cards.encode_query({"AS", "KS"}, {"2C", "7D", "KH"})
+    assert sorted(hole.tolist()) == [47, 51] and board.tolist()[3:] == [255, 255] and len(board) == 5
+    with pytest.raises(ValueError):
+        cards.encode_query(["AS", "KS"], ["XX"])                        # reference: list.index raises ValueError
+    with pytest.raises(ValueError):
+        cards.encode_query(["AS", "AS"], [])
+    with pytest.raises(IndexError):
+        npk.get_equity({"AS", "KS"}, set(), 0, 10)                      # reference: IndexError for players == 0
+
+
+def test_philox_model_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    f = sampler_model.philox4x32_10
+    assert f((0, 0, 0, 0), (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert f((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert f((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_sampler_model_is_consistent_with_enumeration(golden_enum):
+    """The specified uniform sampler (Philox + Fisher-Yates) converges to the exact equity; the specified reference
+    sampler converges to the exact expectation of the reference's biased dealer."""
+    import oracle
+    spot = next(s for s in golden_enum["spots"] if s["name"] == "t16")
+    hole, board = [npk.card_id(c) for c in spot["hero"]], [npk.card_id(c) for c in spot["board"]]
+    runs = 6000
+    w, t, l = spot["uniform"]
+    p = (w + t) / (w + t + l)
+    r = sampler_model.run_model(oracle, "uniform", 11, 0, hole, board, 2, runs)
+    assert abs((r["wins"] + r["ties"]) / runs - p) < 4 * (p * (1 - p) / runs) ** 0.5
+    num, den = spot["reference_mode"]
+    p = num / den
+    r = sampler_model.run_model(oracle, "reference", 11, 0, hole, board, 2, runs)
+    assert abs((r["wins"] + r["ties"]) / runs - p) < 4 * (p * (1 - p) / runs) ** 0.5
+    assert sum(r["win_types"]) == r["wins"] + r["ties"]
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(_lib.NpkError) as e:
+        npk.get_equity({"AS", "KS"}, set(), 2, 100)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    with pytest.raises(_lib.NpkError):
+        npk.montecarlo({"AS", "KS"}, {"null"}, 2, 100)
+
+
+def test_product_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under neuron_poker_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "neuron_poker_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
