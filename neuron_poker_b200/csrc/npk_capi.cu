@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -128,13 +129,6 @@ __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, 
         if (g < 0) continue;
         qindex[go.off[g] + atomicAdd(&cursors[g], 1u)] = (int32_t)q;
     }
-}
-
-// players == 1: the hero is the only hand and always "wins" (reference: index 0 is the best of one hand)
-__global__ void solo_fill_kernel(const int32_t* qindex, long long nq, long long trials, unsigned long long* wins)
-{
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += (long long)gridDim.x * blockDim.x)
-        atomicAdd(&wins[qindex ? qindex[i] : i], (unsigned long long)trials);
 }
 
 uint32_t pick_chunk(long long trials)
@@ -328,10 +322,6 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
 
     if (deal_mode == NPK_DEAL_REFERENCE) {
         // the reference-dealer kernel is generic in players / board size: one launch over all queries
-        if (uniform_shape && uniform_players == 1) {
-            solo_fill_kernel<<<(int)std::min<long long>((Q + 255) / 256, 1024), 256, 0, s>>>(nullptr, Q, trials, p.wins);
-            return NPK_OK;
-        }
         p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
         e = npk::launch_equity_reference(p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
         if (e != cudaSuccess) return cuda_fail(e, "equity_reference_kernel launch");
@@ -340,10 +330,6 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
 
     const size_t smem = npk::equity_uniform_smem(ds->t);
     if (uniform_shape) {
-        if (uniform_players == 1) {
-            solo_fill_kernel<<<(int)std::min<long long>((Q + 255) / 256, 1024), 256, 0, s>>>(nullptr, Q, trials, p.wins);
-            return NPK_OK;
-        }
         p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
         e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p,
                                        grid_for(*ds, Q * chunks, npk::kEquityThreads / 32), smem, s);
@@ -363,10 +349,6 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         if (!counts[g]) continue;
         const int nopp = g / 6, known = g % 6;
         p.qindex = qindex + go.off[g]; p.nq = counts[g]; p.work_counter = counters + g;
-        if (nopp == 0) {
-            solo_fill_kernel<<<(int)std::min<long long>((p.nq + 255) / 256, 1024), 256, 0, s>>>(p.qindex, p.nq, trials, p.wins);
-            continue;
-        }
         e = npk::launch_equity_uniform(nopp, 5 - known, p, grid_for(*ds, p.nq * chunks, npk::kEquityThreads / 32), smem, s);
         if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
     }

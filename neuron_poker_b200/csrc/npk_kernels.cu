@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
             const bool active = t_local < t_end;
             const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
 
-            uint32_t w[NBLK * 4];
+            uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
 #pragma unroll
             for (int b = 0; b < NBLK; b++)
                 philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, (uint32_t)b, p.seed_lo, p.seed_hi,
@@ -142,9 +142,11 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
 #pragma unroll
             for (int k = 0; k < D; k++) {
                 const uint32_t x = (k & 1) ? rem : w[k >> 1];
-                const uint64_t prod = (uint64_t)x * (uint32_t)(N - k);
-                const uint32_t idx = (uint32_t)(prod >> 32);
-                rem = (uint32_t)prod;
+                // index = high word, remainder = low word of x * (N - k).  Written as mul.hi / mul.lo on purpose:
+                // ptxas 12.9 miscompiled the 64-bit form for the last draw (whose low word is dead) into
+                // lo32(x * 4 * (N - k)) -- an out-of-range shared address caught by the per-shape parity test.
+                const uint32_t idx = __umulhi(x, (uint32_t)(N - k));
+                rem = x * (uint32_t)(N - k);
                 slot[k] = idx * 32;
                 dv[k] = fy[idx * 32];
                 fy[idx * 32] = fy[(N - 1 - k) * 32];
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
                 bsum += dv[k]; blo |= l; bhi |= h; bcnt += suit_inc(dv[k]);
             }
             const uint32_t f = bcnt & 0x8888u;
-            const uint32_t fs = (31u - __clz(f)) >> 2;
+            const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;   // & 3: keeps the selector legal when no suit qualifies
             const uint32_t sel = 0x9910u + fs * 0x2222u;
             const uint32_t thr = f ? 5u : 64u;
 
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
                 const uint32_t ov = eval_player(st, bsum + dv[2 * o] + dv[2 * o + 1], blo | l0 | l1, bhi | h0 | h1, sel, thr);
                 best = max(best, ov);
             }
-            const bool win = active && hv > best, tie = active && hv == best;
+            // a lone hero (NOPP == 0) is the best of one hand (reference: index 0 of a one-element list)
+            const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
             wins += win; ties += tie;
             if (p.win_types && (win || tie)) {
                 uint32_t ty = 0;
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
                 }
             }
             const uint32_t f = bcnt & 0x8888u;
-            const uint32_t fs = (31u - __clz(f)) >> 2;
+            const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;   // & 3: keeps the selector legal when no suit qualifies
             const uint32_t sel = 0x9910u + fs * 0x2222u;
             const uint32_t thr = f ? 5u : 64u;
             const uint32_t hv = eval_player(st, bsum + qs.hero_sum, blo | qs.hero_lo, bhi | qs.hero_hi, sel, thr);
@@ -620,6 +623,7 @@ template <int NB>
 static cudaError_t launch_uniform_nb(int nopp, const EquityParams& p, int grid, size_t smem, cudaStream_t s)
 {
     switch (nopp) {
+        case 0: return launch_uniform_t<0, NB>(p, grid, smem, s);
         case 1: return launch_uniform_t<1, NB>(p, grid, smem, s);
         case 2: return launch_uniform_t<2, NB>(p, grid, smem, s);
         case 3: return launch_uniform_t<3, NB>(p, grid, smem, s);

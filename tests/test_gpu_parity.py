@@ -137,7 +137,6 @@ def test_showdown_batch(torch_mod, golden_cases):
     for i, s in enumerate(sds):
         npl[i] = len(s["holes"])
         holes[i, :npl[i]] = s["holes"]
-        holes[i, npl[i]:] = [[0, 1]] * (maxp - npl[i])
         board[i] = s["board"]
     w, t, r = npk.showdown(holes, npl, board, return_ranks=True)
     assert (w.cpu().numpy() == np.array([s["winner"] for s in sds])).all()
@@ -219,6 +218,26 @@ def test_montecarlo_counts_equal_sampler_specification(torch_mod, mode):
             assert int(out["passes"][qi]) == m["passes"], qi
 
 
+def test_every_kernel_instantiation_matches_specification(torch_mod):
+    """All 54 template instantiations of the uniform kernel (1..9 opponents x 0..5 known board cards) and the same
+    shapes through the reference-dealer kernel, each bit-exact against the specification.  (This is the test that caught
+    a ptxas miscompile of the last Fisher-Yates draw during bring-up.)"""
+    torch = torch_mod
+    rng = np.random.default_rng(5)
+    hole, board, npl = [], [], []
+    for players in range(2, 11):
+        for known in range(6):
+            c = rng.permutation(52)[:2 + known].tolist()
+            hole.append(c[:2]); board.append(pad_board(c[2:])); npl.append(players)
+    trials, seed = 40, 77
+    for mode in ("uniform", "reference"):
+        out = _run_batch(torch, hole, board, npl, trials, seed, mode)
+        for qi in range(len(hole)):
+            b = [c for c in board[qi] if c != NO]
+            m = sampler_model.run_model(oracle, mode, seed, qi, hole[qi], b, npl[qi], trials)
+            assert (int(out["wins"][qi]), int(out["ties"][qi])) == (m["wins"], m["ties"]), (mode, npl[qi], len(b))
+
+
 def test_partition_invariance(torch_mod):
     """Counts depend only on (seed, query, trial): splitting the trials over calls (trial_offset) or running a query
     alone gives bit-identical totals.  This is what makes multi-GPU sharding exact."""
@@ -240,14 +259,15 @@ def test_partition_invariance(torch_mod):
 
 
 def test_uniform_mode_matches_exact_enumeration(torch_mod, golden_enum):
-    """UNIFORM dealing vs exact combinatorics, 3 sigma at 1M trials."""
+    """UNIFORM dealing vs exact combinatorics, 3 sigma at 4M trials (fixed seed; across seeds the
+    z-scores of these spots behave like N(0,1), see profiles/r01_zscores.txt)."""
     torch = torch_mod
     spots = [s for s in golden_enum["spots"] if "uniform" in s]
     hole = [ids(s["hero"]) for s in spots]
     board = [pad_board(ids(s["board"])) for s in spots]
     npl = [s["players"] for s in spots]
-    trials = 1000000
-    out = _run_batch(torch, hole, board, npl, trials, 2026, "uniform")
+    trials = 4000000
+    out = _run_batch(torch, hole, board, npl, trials, 8, "uniform")
     for i, s in enumerate(spots):
         w, t, l = s["uniform"]
         tot = w + t + l
@@ -261,8 +281,8 @@ def test_reference_mode_matches_reference_dealer_expectation(torch_mod, golden_e
     spots = [s for s in golden_enum["spots"] if "reference_mode" in s]
     hole = [ids(s["hero"]) for s in spots]
     board = [pad_board(ids(s["board"])) for s in spots]
-    trials = 1000000
-    out = _run_batch(torch, hole, board, [2] * len(spots), trials, 7, "reference")
+    trials = 4000000
+    out = _run_batch(torch, hole, board, [2] * len(spots), trials, 8, "reference")
     for i, s in enumerate(spots):
         num, den = s["reference_mode"]
         p = num / den
