@@ -133,8 +133,11 @@ __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, 
 
 uint32_t pick_chunk(long long trials)
 {
-    if (trials <= 1024) return (uint32_t)(trials > 0 ? trials : 1);
-    return 1024;
+    long long c = getenv("NPK_CHUNK") ? atoll(getenv("NPK_CHUNK")) : 2048;   // trials per work item (<= 64 per lane)
+    if (c < 32) c = 32;
+    if (c > 2048) c = 2048;
+    if (trials <= c) return (uint32_t)(trials > 0 ? trials : 1);
+    return (uint32_t)c;
 }
 
 int grid_for(const DeviceState& ds, long long items, int warps_per_cta)
@@ -328,11 +331,10 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         return NPK_OK;
     }
 
-    const size_t smem = npk::equity_uniform_smem(ds->t);
+    const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;   // tuning aid
     if (uniform_shape) {
         p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
-        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p,
-                                       grid_for(*ds, Q * chunks, npk::kEquityThreads / 32), smem, s);
+        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p, Q * chunks, ds->sm_count, forced_warps, s);
         if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
         return NPK_OK;
     }
@@ -349,7 +351,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         if (!counts[g]) continue;
         const int nopp = g / 6, known = g % 6;
         p.qindex = qindex + go.off[g]; p.nq = counts[g]; p.work_counter = counters + g;
-        e = npk::launch_equity_uniform(nopp, 5 - known, p, grid_for(*ds, p.nq * chunks, npk::kEquityThreads / 32), smem, s);
+        e = npk::launch_equity_uniform(nopp, 5 - known, p, p.nq * chunks, ds->sm_count, forced_warps, s);
         if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
     }
     return NPK_OK;

@@ -4,7 +4,7 @@
 //   g_value   u16[n_value]   rank ids, row-displaced:  value[row_offset[mk >> 10] + (mk & 1023)]
 //   g_rowoff  u16[8192]      one offset per row of the mixed key mk (23 bits)
 //   g_flush   u16[8192]      rank id by 13-bit rank mask of the flush suit
-//   g_desc    u32[52]        per-card descriptor  d = (mixkey[rank] << 9) | (16*suit + rank)
+//   g_desc    u32[52]        per-card descriptor  d = (mixkey[rank] << 9) | (16*suit + 12 - rank)
 // Summing the descriptors of 7 cards with ordinary 32-bit wrap-around adds gives  total = (mk << 9) | psum  where
 // mk = sum of mixed rank keys mod 2^23 identifies the rank histogram and psum < 512 never carries into mk.
 // The three tables (about 129 KB) are copied once per CTA into shared memory with the bulk-copy engine (TMA 1-D).
@@ -14,7 +14,7 @@
 
 namespace npk {
 
-constexpr int kDevDescShift = 9;   // descriptor: bits 9..31 mixed rank key, bits 0..5 suit-major card position
+constexpr int kDevDescShift = 9;   // descriptor: bits 9..31 mixed rank key, bits 4..5 suit, bits 0..3 = 12 - rank
 constexpr int kRowBits = 10;       // column bits of the mixed key   (== npk_tables.h kDescShift / kRowShift,
 constexpr uint32_t kColMask = (1u << kRowBits) - 1u;   //              checked by a static_assert in npk_capi.cu)
 
@@ -119,18 +119,51 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 
 // ---- evaluator -----------------------------------------------------------------------------------------------------
-// rank id of a hand WITHOUT a flush from the wrapped sum of its 7 card descriptors
-__device__ __forceinline__ uint32_t lookup_nonflush(const SmemTables& s, uint32_t total)
+// PTX shr / shl clamp shift amounts above 31 to 32 (result 0), unlike the C++ operators whose behaviour is undefined.
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n)
 {
-    uint32_t off = s.rowoff[total >> (kDevDescShift + kRowBits)];
-    uint32_t col = (total >> kDevDescShift) & kColMask;
-    return s.value[off + col];
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
 }
+
+// 16-bit gather from shared memory by 32-bit shared address, zero-extended into a full register (keeps ptxas from
+// switching to packed 16x2 arithmetic and the PRMT traffic that comes with it)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
+{
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+struct SmemAddr {          // 32-bit shared-window addresses of the staged tables
+    uint32_t value, rowoff, flush;
+};
+
+__device__ __forceinline__ SmemAddr smem_addr(const SmemTables& s)
+{
+    SmemAddr a;
+    a.value = smem_u32(s.value); a.rowoff = smem_u32(s.rowoff); a.flush = smem_u32(s.flush);
+    return a;
+}
+
+// rank id of a hand WITHOUT a flush from the wrapped sum of its 7 card descriptors.
+// The two constant right shifts are written as multiply-high so they issue on the (otherwise idle) fma pipe.
+__device__ __forceinline__ uint32_t lookup_nonflush(const SmemAddr& a, uint32_t total)
+{
+    const uint32_t row2 = __umulhi(total, 1u << (32 - (kDevDescShift + kRowBits - 1))) & (0xFFFFu << 1);   // 2*row
+    const uint32_t off = lds_u16(a.rowoff + row2);
+    const uint32_t col2 = __umulhi(total, 1u << (32 - (kDevDescShift - 1))) & (kColMask << 1);              // 2*col
+    return lds_u16(a.value + col2 + (off << 1));
+}
+
+// contribution of a card to the 13-bit rank mask of suit fs (fsx = fs << 4): 1 << rank if the suit matches, else 0
+__device__ __forceinline__ uint32_t flush_bit(uint32_t d, uint32_t fsx) { return shr_clamp(0x1000u, (d ^ fsx) & 63u); }
 
 // 64-bit suit-major one-hot of a card descriptor: bit 16*suit + rank
 __device__ __forceinline__ void card_bits(uint32_t d, uint32_t& lo, uint32_t& hi)
 {
-    uint64_t b = 1ull << (d & 63u);
+    const uint64_t b = 1ull << ((d & 0x30u) + 12u - (d & 15u));
     lo = (uint32_t)b;
     hi = (uint32_t)(b >> 32);
 }
@@ -138,9 +171,13 @@ __device__ __forceinline__ void card_bits(uint32_t d, uint32_t& lo, uint32_t& hi
 // nibble-per-suit counter increment of a card descriptor: 1 << 4*suit
 __device__ __forceinline__ uint32_t suit_inc(uint32_t d) { return 1u << ((d >> 2) & 12u); }
 
-// Plain 7-card evaluation from card ids (used by rank7 / showdown / enumeration kernels, not by the Monte-Carlo loop,
-// which carries the board part across players).
-__device__ __forceinline__ uint32_t eval7_desc(const SmemTables& s, const uint32_t d[7])
+// PRMT selector that extracts the 16-bit field of suit fs from a (lo, hi) suit-major pair and zeroes the upper half
+// (selector nibble 8|k replicates the sign bit of byte k, which is always 0 here: ranks use bits 0..12 of a field)
+__device__ __forceinline__ uint32_t field_selector(uint32_t fs) { return 0x9910u + fs * 0x2222u; }
+
+// Plain 7-card evaluation from card descriptors (rank7 / showdown / enumeration kernels; the Monte-Carlo loops carry the
+// board part across players instead).
+__device__ __forceinline__ uint32_t eval7_desc(const SmemAddr& a, const uint32_t d[7])
 {
     uint32_t total = 0, lo = 0, hi = 0, cnt = 0x3333u;
 #pragma unroll
@@ -152,12 +189,11 @@ __device__ __forceinline__ uint32_t eval7_desc(const SmemTables& s, const uint32
         hi |= h;
         cnt += suit_inc(d[i]);
     }
-    uint32_t v = lookup_nonflush(s, total);
-    uint32_t f = cnt & 0x8888u;                       // nibble >= 8  <=>  that suit holds >= 5 cards
+    uint32_t v = lookup_nonflush(a, total);
+    const uint32_t f = cnt & 0x8888u;                 // nibble >= 8  <=>  that suit holds >= 5 cards
     if (f) {
-        uint32_t fs = (31u - __clz(f)) >> 2;
-        uint32_t field = prmt(lo, hi, 0x9910u + fs * 0x2222u);   // 16-bit field of suit fs, upper half zeroed
-        v = s.flush[field];                           // a flush excludes full house / quads in 7 cards
+        const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;
+        v = lds_u16(a.flush + 2u * prmt(lo, hi, field_selector(fs)));   // a flush excludes full house / quads in 7 cards
     }
     return v;
 }

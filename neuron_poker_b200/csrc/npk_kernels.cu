@@ -30,9 +30,9 @@ __device__ __forceinline__ long long next_item(unsigned long long* counter, int 
 // Per-query constants shared by every trial of a work item.
 struct QueryStatic {
     uint32_t hero_sum;    // desc(h0) + desc(h1)
-    uint32_t hero_lo, hero_hi;
+    uint32_t hero_lo, hero_hi;     // suit-major rank masks (16 bits per suit) of the hero's cards
     uint32_t board_sum;   // sum of known board descriptors
-    uint32_t board_lo, board_hi;
+    uint32_t board_lo, board_hi;   // suit-major rank masks of the known board cards
     uint32_t board_cnt;   // nibble-per-suit counters of known board cards, each biased by 5 (>= 8 <=> >= 3 cards)
     uint64_t known;       // bit per card id (rank-major) of hero + known board cards
 };
@@ -58,14 +58,29 @@ __device__ __forceinline__ QueryStatic load_query(const EquityParams& p, long lo
     return s;
 }
 
-// Flush-aware rank id of (board + two hole cards).  `sel`/`thr` describe the only suit that can still flush on this
-// board (the suit holding >= 3 board cards), thr = 5 or 64 (= impossible).
-__device__ __forceinline__ uint32_t eval_player(const SmemTables& s, uint32_t total, uint32_t lo, uint32_t hi,
-                                                uint32_t sel, uint32_t thr)
+// What a complete board says about flushes: at most one suit (the one holding >= 3 board cards) can still flush.
+struct BoardFlush {
+    uint32_t fsx;     // that suit << 4 (meaningless when thr == 64)
+    uint32_t sel;     // PRMT selector of its 16-bit field
+    uint32_t thr;     // 5 if a flush is possible on this board, else 64 (= never)
+};
+
+__device__ __forceinline__ BoardFlush board_flush(uint32_t board_cnt)
 {
-    uint32_t v = lookup_nonflush(s, total);
-    uint32_t field = prmt(lo, hi, sel);
-    if ((uint32_t)__popc(field) >= thr) v = max(v, (uint32_t)s.flush[field]);
+    BoardFlush b;
+    const uint32_t f = board_cnt & 0x8888u;
+    const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;     // & 3 keeps selector and shift legal when f == 0
+    b.fsx = fs << 4;
+    b.sel = field_selector(fs);
+    b.thr = f ? 5u : 64u;
+    return b;
+}
+
+// Flush-aware rank id: `total` = wrapped descriptor sum of the 7 cards, `field` = rank mask of the candidate flush suit.
+__device__ __forceinline__ uint32_t eval_player(const SmemAddr& a, uint32_t total, uint32_t field, uint32_t thr)
+{
+    uint32_t v = lookup_nonflush(a, total);
+    if ((uint32_t)__popc(field) >= thr) v = max(v, lds_u16(a.flush + 2u * field));
     return v;
 }
 
@@ -83,7 +98,7 @@ __device__ __forceinline__ uint32_t eval_player(const SmemTables& s, uint32_t to
 // draws by multiply-shift with remainder reuse: x*m -> (index, x'), x'*(m-1) -> index; bias < 2^-26 per draw.
 // =====================================================================================================================
 template <int NOPP, int NB>
-__global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const EquityParams p)
+__global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(const EquityParams p)
 {
     constexpr int KNOWN = 5 - NB;
     constexpr int N = 50 - KNOWN;          // unseen cards
@@ -94,11 +109,11 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
 
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
     const uint32_t table_bytes = 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp: 64-word scratch (static deck order) + interleaved deck (52 rows x 32 lanes)
-    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + 52 * 32);
+    // per-warp: 64-word scratch (static deck order) + interleaved deck (N rows x 32 lanes)
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + N * 32);
     uint32_t* fy = scratch + 64 + lane;
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
@@ -154,27 +169,21 @@ __global__ void __launch_bounds__(kEquityThreads, 1) equity_uniform_kernel(const
 #pragma unroll
             for (int k = D - 1; k >= 0; k--) fy[slot[k]] = dv[k];
 
-            // board
-            uint32_t bsum = qs.board_sum, blo = qs.board_lo, bhi = qs.board_hi, bcnt = qs.board_cnt;
+            // board: descriptor sum, suit counters -> the one suit that can still flush, its rank mask
+            uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
 #pragma unroll
-            for (int k = 2 * NOPP; k < D; k++) {
-                uint32_t l, h;
-                card_bits(dv[k], l, h);
-                bsum += dv[k]; blo |= l; bhi |= h; bcnt += suit_inc(dv[k]);
-            }
-            const uint32_t f = bcnt & 0x8888u;
-            const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;   // & 3: keeps the selector legal when no suit qualifies
-            const uint32_t sel = 0x9910u + fs * 0x2222u;
-            const uint32_t thr = f ? 5u : 64u;
+            for (int k = 2 * NOPP; k < D; k++) { bsum += dv[k]; bcnt += suit_inc(dv[k]); }
+            const BoardFlush bf = board_flush(bcnt);
+            uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
+#pragma unroll
+            for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[k], bf.fsx);
 
-            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, blo | qs.hero_lo, bhi | qs.hero_hi, sel, thr);
+            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
             uint32_t best = 0;
 #pragma unroll
             for (int o = 0; o < NOPP; o++) {
-                uint32_t l0, h0, l1, h1;
-                card_bits(dv[2 * o], l0, h0);
-                card_bits(dv[2 * o + 1], l1, h1);
-                const uint32_t ov = eval_player(st, bsum + dv[2 * o] + dv[2 * o + 1], blo | l0 | l1, bhi | h0 | h1, sel, thr);
+                const uint32_t d0 = dv[2 * o], d1 = dv[2 * o + 1];
+                const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
                 best = max(best, ov);
             }
             // a lone hero (NOPP == 0) is the best of one hand (reference: index 0 of a one-element list)
@@ -245,7 +254,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
     const int lane = threadIdx.x & 31;
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
@@ -278,14 +287,14 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
             uint64_t avail = avail0;
             int n = n0;
             uint32_t best = 0;
-            uint32_t osum[9], olo[9], ohi[9];
+            uint32_t oc1[9], oc2[9];
             if (active) {
                 for (int o = 0; o < nopp; o++) {
                     uint32_t i1, i2;
                     do {
                         const uint64_t prod = (uint64_t)rs.next() * (uint32_t)n;
                         i1 = (uint32_t)(prod >> 32);
-                        i2 = (uint32_t)(((uint64_t)(uint32_t)prod * (uint32_t)(n - 1)) >> 32);
+                        i2 = __umulhi((uint32_t)prod, (uint32_t)(n - 1));
                         passes++;
                     } while (i1 == i2);
                     const int c1 = select_bit(avail, (int)i1);
@@ -293,34 +302,32 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
                     const int c2 = select_bit(avail, (int)i2);
                     avail &= ~(1ull << c2);
                     n -= 2;
-                    const uint32_t d1 = p.tables.desc[c1], d2 = p.tables.desc[c2];
-                    uint32_t l1, h1, l2, h2;
-                    card_bits(d1, l1, h1);
-                    card_bits(d2, l2, h2);
-                    osum[o] = d1 + d2; olo[o] = l1 | l2; ohi[o] = h1 | h2;
+                    oc1[o] = p.tables.desc[c1];
+                    oc2[o] = p.tables.desc[c2];
                 }
             }
-            uint32_t bsum = qs.board_sum, blo = qs.board_lo, bhi = qs.board_hi, bcnt = qs.board_cnt;
+            uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
+            uint32_t bd[5];
+            int nbd = 0;
             if (active) {
                 for (int k = known; k < 5; k++) {
-                    const uint32_t j = (uint32_t)(((uint64_t)rs.next() * (uint32_t)(n - 1)) >> 32);
+                    const uint32_t j = __umulhi(rs.next(), (uint32_t)(n - 1));
                     const int c = select_bit(avail, (int)j);
                     avail &= ~(1ull << c);
                     n--;
                     const uint32_t d = p.tables.desc[c];
-                    uint32_t l, h;
-                    card_bits(d, l, h);
-                    bsum += d; blo |= l; bhi |= h; bcnt += suit_inc(d);
+                    bd[nbd++] = d;
+                    bsum += d; bcnt += suit_inc(d);
                 }
             }
-            const uint32_t f = bcnt & 0x8888u;
-            const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;   // & 3: keeps the selector legal when no suit qualifies
-            const uint32_t sel = 0x9910u + fs * 0x2222u;
-            const uint32_t thr = f ? 5u : 64u;
-            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, blo | qs.hero_lo, bhi | qs.hero_hi, sel, thr);
+            const BoardFlush bf = board_flush(bcnt);
+            uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
+            for (int k = 0; k < nbd; k++) bfield |= flush_bit(bd[k], bf.fsx);
+            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
             if (active)
                 for (int o = 0; o < nopp; o++)
-                    best = max(best, eval_player(st, bsum + osum[o], blo | olo[o], bhi | ohi[o], sel, thr));
+                    best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
+                                                 bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
             // a lone hero (players == 1) is the best of one hand (reference: index 0 of a one-element list)
             const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
             wins += win; ties += tie;
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(kAuxThreads, 1) rank7_kernel(const DeviceTable
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
     uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
     if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
     __syncthreads();
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(kAuxThreads, 1) rank7_colex_kernel(const Devic
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
     uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
     if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
     __syncthreads();
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(p.tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
     uint8_t* extra = smem + 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
     uint32_t* s_deck = reinterpret_cast<uint32_t*>(extra);            // [52] descriptors of unseen cards
     uint16_t* s_pairval = reinterpret_cast<uint16_t*>(extra + 256);   // [1326] rank of each opponent pair (river)
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(kAuxThreads, 1) showdown_kernel(const DeviceTa
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const SmemTables st = stage_tables(tables, smem + 128, bar);
+    const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
     uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
     if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
     __syncthreads();
@@ -609,50 +616,64 @@ cudaError_t launch_int_peak(int variant, uint32_t* out, int iters, int grid, cud
 // ---------------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------------
+// Shared memory decides the CTA shape: tables + one private deck per warp.  As many warps as fit (at most 16) run on
+// each SM; the deck of N = 45..50 cards costs 128 B per card per warp.
+static int uniform_warps(const DeviceTables& t, int nb, int forced)
+{
+    const size_t fixed = 128 + (size_t)t.value_bytes + t.rowoff_bytes + t.flush_bytes;
+    const size_t per_warp = (size_t)(64 + (45 + nb) * 32) * 4;
+    int w = (int)((kMaxDynamicSmem - fixed) / per_warp);
+    if (w > kEquityMaxThreads / 32) w = kEquityMaxThreads / 32;
+    if (forced > 0 && forced < w) w = forced;
+    return w < 1 ? 1 : w;
+}
+
 template <int NOPP, int NB>
-static cudaError_t launch_uniform_t(const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+static cudaError_t launch_uniform_t(const EquityParams& p, long long items, int sm_count, int forced_warps, cudaStream_t s)
 {
     auto k = equity_uniform_kernel<NOPP, NB>;
+    const int warps = uniform_warps(p.tables, NB, forced_warps);
+    const size_t smem = 128 + (size_t)p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes +
+                        (size_t)warps * (64 + (45 + NB) * 32) * 4;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, kEquityThreads, smem, s>>>(p);
+    long long grid = (items + warps - 1) / warps;
+    if (grid < 1) grid = 1;
+    if (grid > sm_count) grid = sm_count;
+    k<<<(int)grid, warps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 template <int NB>
-static cudaError_t launch_uniform_nb(int nopp, const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+static cudaError_t launch_uniform_nb(int nopp, const EquityParams& p, long long items, int sm_count, int fw, cudaStream_t s)
 {
     switch (nopp) {
-        case 0: return launch_uniform_t<0, NB>(p, grid, smem, s);
-        case 1: return launch_uniform_t<1, NB>(p, grid, smem, s);
-        case 2: return launch_uniform_t<2, NB>(p, grid, smem, s);
-        case 3: return launch_uniform_t<3, NB>(p, grid, smem, s);
-        case 4: return launch_uniform_t<4, NB>(p, grid, smem, s);
-        case 5: return launch_uniform_t<5, NB>(p, grid, smem, s);
-        case 6: return launch_uniform_t<6, NB>(p, grid, smem, s);
-        case 7: return launch_uniform_t<7, NB>(p, grid, smem, s);
-        case 8: return launch_uniform_t<8, NB>(p, grid, smem, s);
-        case 9: return launch_uniform_t<9, NB>(p, grid, smem, s);
+        case 0: return launch_uniform_t<0, NB>(p, items, sm_count, fw, s);
+        case 1: return launch_uniform_t<1, NB>(p, items, sm_count, fw, s);
+        case 2: return launch_uniform_t<2, NB>(p, items, sm_count, fw, s);
+        case 3: return launch_uniform_t<3, NB>(p, items, sm_count, fw, s);
+        case 4: return launch_uniform_t<4, NB>(p, items, sm_count, fw, s);
+        case 5: return launch_uniform_t<5, NB>(p, items, sm_count, fw, s);
+        case 6: return launch_uniform_t<6, NB>(p, items, sm_count, fw, s);
+        case 7: return launch_uniform_t<7, NB>(p, items, sm_count, fw, s);
+        case 8: return launch_uniform_t<8, NB>(p, items, sm_count, fw, s);
+        case 9: return launch_uniform_t<9, NB>(p, items, sm_count, fw, s);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, int grid, size_t smem, cudaStream_t s)
+cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
+                                  cudaStream_t s)
 {
     switch (nb) {
-        case 0: return launch_uniform_nb<0>(nopp, p, grid, smem, s);
-        case 1: return launch_uniform_nb<1>(nopp, p, grid, smem, s);
-        case 2: return launch_uniform_nb<2>(nopp, p, grid, smem, s);
-        case 3: return launch_uniform_nb<3>(nopp, p, grid, smem, s);
-        case 4: return launch_uniform_nb<4>(nopp, p, grid, smem, s);
-        case 5: return launch_uniform_nb<5>(nopp, p, grid, smem, s);
+        case 0: return launch_uniform_nb<0>(nopp, p, items, sm_count, forced_warps, s);
+        case 1: return launch_uniform_nb<1>(nopp, p, items, sm_count, forced_warps, s);
+        case 2: return launch_uniform_nb<2>(nopp, p, items, sm_count, forced_warps, s);
+        case 3: return launch_uniform_nb<3>(nopp, p, items, sm_count, forced_warps, s);
+        case 4: return launch_uniform_nb<4>(nopp, p, items, sm_count, forced_warps, s);
+        case 5: return launch_uniform_nb<5>(nopp, p, items, sm_count, forced_warps, s);
         default: return cudaErrorInvalidValue;
     }
-}
-
-size_t equity_uniform_smem(const DeviceTables& t)
-{
-    return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + (size_t)(kEquityThreads / 32) * (64 + 52 * 32) * 4;
 }
 
 size_t aux_smem(const DeviceTables& t) { return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + 256 + 1326 * 2 + 64; }

@@ -6,7 +6,8 @@
 
 namespace npk {
 
-constexpr int kEquityThreads = 384;   // 12 warps per CTA, one CTA per SM (shared memory bound)
+constexpr int kEquityMaxThreads = 512; // up to 16 warps per CTA, one CTA per SM (shared memory decides, see uniform_warps)
+constexpr size_t kMaxDynamicSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 constexpr int kRefThreads = 512;
 constexpr int kAuxThreads = 512;
 
@@ -40,9 +41,9 @@ struct EnumParams {
     unsigned long long* lose;
 };
 
-size_t equity_uniform_smem(const DeviceTables& t);
 size_t aux_smem(const DeviceTables& t);
-cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, int grid, size_t smem, cudaStream_t s);
+cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
+                                  cudaStream_t s);
 cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);

@@ -16,7 +16,7 @@ constexpr int kNumHistograms = 49205;
 constexpr int kRowShift = 10;            // row = mk >> kRowShift, column = mk & (2^kRowShift - 1), mk = mixed key
 constexpr int kMixBits = 23;             // mixed keys live modulo 2^23 (> largest plain key sum 7,825,759)
 constexpr uint32_t kMixMul = 0x9E3779B1u; // odd multiplier: mk = (kMixMul * plain key) mod 2^23 scatters the rows
-constexpr int kDescShift = 9;            // card descriptor = (mixed rank key << 9) | (16*suit + rank)
+constexpr int kDescShift = 9;            // card descriptor = (mixed rank key << 9) | (16*suit + (12 - rank))
 constexpr int kFlushTableSize = 8192;    // indexed by the 13-bit rank mask of the flush suit
 
 // additive rank keys: key(hand) = sum over the 7 cards of kRankKey[rank]; distinct for distinct rank histograms
@@ -27,7 +27,10 @@ constexpr int kFlushTableSize = 8192;    // indexed by the 13-bit rank mask of t
 extern const uint32_t kRankKey[kNumRanks];
 inline uint32_t mixed_rank_key(int rank) { return (kMixMul * kRankKey[rank]) & ((1u << kMixBits) - 1u); }
 // 32-bit card descriptor for card id = 4*rank + suit (reference deck order, montecarlo_python.py:114-119)
-inline uint32_t card_desc(int card) { return (mixed_rank_key(card >> 2) << kDescShift) | (uint32_t)(16 * (card & 3) + (card >> 2)); }
+// The low 6 bits hold the suit (bits 4-5) and the REVERSED rank 12 - rank (bits 0-3): the device turns a card into its
+// contribution to the rank mask of suit fs with one XOR-AND and one clamped shift, 0x1000 >> ((d ^ (fs << 4)) & 63),
+// which is 1 << rank when the suit matches and 0 otherwise.
+inline uint32_t card_desc(int card) { return (mixed_rank_key(card >> 2) << kDescShift) | (uint32_t)(16 * (card & 3) + 12 - (card >> 2)); }
 
 // first rank_id of each hand type, in the reference's type order:
 // HighCard, Pair, TwoPair, ThreeOfAKind, Straight, Flush, FullHouse, FoufOfAKind, StraightFlush, (end)
