@@ -131,9 +131,15 @@ __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, 
     }
 }
 
-uint32_t pick_chunk(long long trials)
+// Trials per work item.  Large jobs use 2,048 (64 trials per lane: the per-item set-up -- query load, deck
+// initialisation, reduction -- is then about 2 % of the work); small jobs are cut finer so that a single query still
+// spreads over the whole chip (a lone get_equity call of 10,000 trials becomes 313 one-iteration items).
+uint32_t pick_chunk(long long queries, long long trials, int sm_count)
 {
-    long long c = getenv("NPK_CHUNK") ? atoll(getenv("NPK_CHUNK")) : 2048;   // trials per work item (<= 64 per lane)
+    const long long warps = (long long)sm_count * 16;
+    long long c = (queries * trials) / (4 * warps);
+    if (getenv("NPK_CHUNK")) c = atoll(getenv("NPK_CHUNK"));      // tuning aid
+    c = (c + 31) / 32 * 32;
     if (c < 32) c = 32;
     if (c > 2048) c = 2048;
     if (trials <= c) return (uint32_t)(trials > 0 ? trials : 1);
@@ -297,7 +303,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(trials);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);

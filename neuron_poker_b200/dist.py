@@ -66,9 +66,8 @@ def sharded_equity(hole, board, n_players, trials, seed_value=0, deal_mode="unif
         from .equity import get_equity_batch
 
         def run(h, b, p, t, trial_offset, first_query):
-            # queries keep their GLOBAL ids in the Philox counter: pass the whole batch and let qindex select? The C ABI
-            # numbers queries by their position in the arrays, so a query shard is passed as a view starting at the
-            # same global position: rows outside the shard are given zero trials by running only the slice below.
+            # a query shard is numbered from `first_query` in the Philox counter (query_offset), a trial shard from
+            # `trial_offset`: the shard reproduces exactly the numbers the whole job would have produced for it
             out = get_equity_batch(h, b, p, t, seed_value=seed_value, deal_mode=deal_mode, trial_offset=trial_offset,
                                    uniform_shape=uniform_shape, validate=False, query_offset=first_query)
             return out["wins"], out["ties"]

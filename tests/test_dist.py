@@ -1,0 +1,79 @@
+"""Sharding of the equity path over ranks, checked on CPU with gloo (world size 2).
+
+The per-rank worker is a CPU stand-in for the GPU kernel -- the executable sampler specification scored by the oracle --
+so what is tested here is the host-side algebra of neuron_poker_b200.dist: query blocks need no collective and gather
+back in order; trial ranges are combined by one all-reduce; both reproduce the unsharded counts bit for bit because the
+Philox counters carry global (query, trial) numbers."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neuron_poker_b200 import dist as npk_dist
+
+QUERIES = [([51, 47], [0, 21, 46], 6), ([12, 13], [], 2), ([30, 31], [1, 2, 3, 4], 3), ([8, 40], [5, 6, 7, 9, 10], 4),
+           ([20, 25], [11, 14, 15], 2)]
+TRIALS, SEED = 48, 2026
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _model_counts(first_query, queries, trials, trial_offset):
+    import oracle
+    import sampler_model
+    wins, ties = [], []
+    for i, (h, b, p) in enumerate(queries):
+        m = sampler_model.run_model(oracle, "uniform", SEED, first_query + i, h, b, p, trials, trial_offset=trial_offset)
+        wins.append(m["wins"])
+        ties.append(m["ties"])
+    return torch.tensor(wins, dtype=torch.int64), torch.tensor(ties, dtype=torch.int64)
+
+
+def _worker(rank, world, port, by, ret):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    hole = [q[0] for q in QUERIES]
+    board = [q[1] for q in QUERIES]
+    npl = [q[2] for q in QUERIES]
+
+    def run(h, b, p, t, trial_offset, first_query):
+        return _model_counts(first_query, list(zip(h, b, p)), t, trial_offset)
+
+    wins, ties = npk_dist.sharded_equity(hole, board, npl, TRIALS, seed_value=SEED, by=by, run=run)
+    ret[rank] = (wins.tolist(), ties.tolist())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("by", ["query", "trial"])
+def test_sharded_counts_equal_unsharded(by):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), by, ret), nprocs=world, join=True)
+    ref_w, ref_t = _model_counts(0, QUERIES, TRIALS, 0)
+    for r in range(world):
+        assert ret[r] == (ref_w.tolist(), ref_t.tolist()), (by, r)
+
+
+def test_shard_arithmetic():
+    for n in (0, 1, 5, 169, 4096, 10000):
+        for world in (1, 2, 3, 8):
+            spans = [npk_dist.query_shard(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+            assert sum(c for _, c in (npk_dist.trial_shard(n, r, world) for r in range(world))) == n
