@@ -554,3 +554,112 @@ int oracle_enum_reference_headsup(const uint8_t *hero, const uint8_t *board, int
     out[0] = num; out[1] = den;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Exhaustive enumeration support: all C(52,7) = 133,784,560 hands in colexicographic order (c0 < ... < c6,
+ * index = sum_i C(c_i, i+1)), the order of libnpk's npk_rank7_colex.
+ * oracle_rank7_fast() is the SAME function as oracle_rank7() tabulated: the rank id of every rank histogram and of
+ * every flush mask is computed once with oracle_calc_score (above) and then looked up; tests/test_oracle.py checks
+ * fast == slow on seeded hands.
+ * ---------------------------------------------------------------------------------------------------------------- */
+#define FAST_HASH_SIZE (1 << 17)
+static uint32_t g_fast_code[FAST_HASH_SIZE];
+static uint16_t g_fast_id[FAST_HASH_SIZE];
+static uint16_t g_fast_flush[8192];
+static int g_fast_ready = 0;
+static const uint32_t POW5[13] = {1, 5, 25, 125, 625, 3125, 15625, 78125, 390625, 1953125, 9765625, 48828125, 244140625};
+
+static void fast_rec(int r, int left, int *h)
+{
+    if (r == 12) {
+        if (left > 4) return;
+        h[12] = left;
+        uint8_t cards[7]; int k = 0; uint32_t code = 0;
+        for (int q = 0; q < 13; q++) {
+            code += (uint32_t)h[q] * POW5[q];
+            for (int j = 0; j < h[q]; j++) { cards[k] = (uint8_t)(4 * q + (k & 3)); k++; }
+        }
+        uint32_t slot = (code * 2654435761u) >> 15;
+        while (g_fast_code[slot] != 0xFFFFFFFFu) slot = (slot + 1) & (FAST_HASH_SIZE - 1);
+        g_fast_code[slot] = code;
+        g_fast_id[slot] = (uint16_t)oracle_rank7(cards);
+        return;
+    }
+    for (int c = 0; c <= 4 && c <= left; c++) { h[r] = c; fast_rec(r + 1, left - c, h); }
+}
+
+void oracle_fast_init(void)
+{
+    if (g_fast_ready) return;
+    oracle_build_classes();
+    memset(g_fast_code, 0xFF, sizeof g_fast_code);
+    int h[13];
+    fast_rec(0, 7, h);
+    for (int mask = 0; mask < 8192; mask++) {
+        int pc = __builtin_popcount(mask);
+        g_fast_flush[mask] = 0xFFFF;
+        if (pc < 5 || pc > 7) continue;
+        uint8_t cards[7]; int k = 0;
+        for (int r = 0; r < 13; r++) if (mask >> r & 1) cards[k++] = (uint8_t)(4 * r);
+        for (int r = 0; k < 7; r++) cards[k++] = (uint8_t)(4 * r + 1);
+        g_fast_flush[mask] = (uint16_t)oracle_rank7(cards);
+    }
+    g_fast_ready = 1;
+}
+
+int oracle_rank7_fast(const uint8_t *cards)
+{
+    uint32_t code = 0, sm[4] = {0, 0, 0, 0};
+    int sc[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 7; i++) {
+        int r = cards[i] >> 2, s = cards[i] & 3;
+        code += POW5[r]; sc[s]++; sm[s] |= 1u << r;
+    }
+    for (int s = 0; s < 4; s++) if (sc[s] >= 5) return g_fast_flush[sm[s]];
+    uint32_t slot = (code * 2654435761u) >> 15;
+    while (g_fast_code[slot] != code) slot = (slot + 1) & (FAST_HASH_SIZE - 1);
+    return g_fast_id[slot];
+}
+
+static int64_t binom64(int n, int k)
+{
+    if (k < 0 || k > n) return 0;
+    int64_t r = 1;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+
+/* ranks of hands first..first+count-1 (colex).  Any of out_ranks / sums may be NULL.
+ * sums[0] += sum of rank ids, sums[1] += sum of rank_id * ((index mod 65521) + 1), sums[2..10] += hand-type census. */
+int oracle_colex_range(int64_t first, int64_t count, uint16_t *out_ranks, int64_t *sums, int use_fast)
+{
+    if (use_fast) oracle_fast_init(); else oracle_build_classes();
+    if (first < 0 || count < 0 || first + count > 133784560LL) return -1;
+    static const int type_start[10] = {0, 407, 1877, 2640, 3215, 3225, 4502, 4658, 4736, 5034};
+    uint8_t c[7];
+    int64_t r = first;
+    int hi = 51;
+    for (int k = 7; k >= 1; k--) {
+        int x = hi;
+        while (binom64(x, k) > r) x--;
+        r -= binom64(x, k);
+        c[k - 1] = (uint8_t)x;
+        hi = x - 1;
+    }
+    for (int64_t i = 0; i < count; i++) {
+        int id = use_fast ? oracle_rank7_fast(c) : oracle_rank7(c);
+        if (out_ranks) out_ranks[i] = (uint16_t)id;
+        if (sums) {
+            sums[0] += id;
+            sums[1] += (int64_t)id * (((first + i) % 65521) + 1);
+            int ty = 0;
+            for (int t = 1; t < 9; t++) ty += id >= type_start[t];
+            sums[2 + ty]++;
+        }
+        /* next combination in colex order: increment the lowest position that can move */
+        int j = 0;
+        while (j < 6 && c[j] + 1 == c[j + 1]) { c[j] = (uint8_t)j; j++; }
+        c[j]++;
+    }
+    return 0;
+}

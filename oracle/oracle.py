@@ -47,6 +47,9 @@ def lib():
         L.oracle_rank7_batch.argtypes = [u8p, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint16)]
         L.oracle_rank7_batch.restype = None
         L.oracle_type7.argtypes = [u8p]
+        L.oracle_rank7_fast.argtypes = [u8p]
+        L.oracle_fast_init.restype = None
+        L.oracle_colex_range.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint16), i64p, ctypes.c_int]
         L.oracle_get_winner.argtypes = [u8p, ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_int)]
         for name in ("oracle_mc_reference", "oracle_mc_uniform"):
             getattr(L, name).argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32, i64p]
@@ -127,6 +130,32 @@ def rank7_batch(cards):
     out = np.empty(len(a), dtype=np.uint16)
     lib().oracle_rank7_batch(_p(a), len(a), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)))
     return out
+
+
+N_HANDS_7 = 133784560
+
+
+def colex_range(first, count, want_ranks=True, fast=True):
+    """(ranks uint16[count] or None, sums int64[11]) of hands first..first+count-1 in colexicographic order.
+    sums = [sum of ids, position-weighted sum, census of the 9 hand types]."""
+    ranks = np.empty(count, dtype=np.uint16) if want_ranks else None
+    sums = np.zeros(11, dtype=np.int64)
+    rc = lib().oracle_colex_range(int(first), int(count),
+                                  ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16)) if want_ranks else None,
+                                  sums.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1 if fast else 0)
+    if rc:
+        raise ValueError("range outside C(52,7)")
+    return ranks, sums
+
+
+def colex_checksums(chunk, threads=8):
+    """Per-chunk sums over ALL C(52,7) hands, computed on `threads` threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib().oracle_fast_init()
+    starts = list(range(0, N_HANDS_7, chunk))
+    with ThreadPoolExecutor(threads) as ex:
+        res = list(ex.map(lambda s: colex_range(s, min(chunk, N_HANDS_7 - s), want_ranks=False)[1], starts))
+    return np.stack(res)
 
 
 def get_winner(holes, board):

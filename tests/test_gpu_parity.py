@@ -85,6 +85,26 @@ def test_rank7_golden_and_oracle(torch_mod, golden_cases, golden_tables):
         assert (npk.rank7(np.array(fc, dtype=np.uint8)).cpu().numpy() == fl[masks]).all()
 
 
+def test_rank7_exhaustive_all_133784560_hands(torch_mod):
+    """Every 7-card hand (colexicographic enumeration on the GPU, no input traffic): per-chunk sum, position-weighted
+    sum and hand-type census equal the oracle's golden checksums; three chunks are also compared id by id."""
+    import json
+    import os
+    torch = torch_mod
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "colex_checksums.json")))
+    chunk, n = gold["chunk"], gold["n_hands"]
+    ts = torch.tensor([0, 407, 1877, 2640, 3215, 3225, 4502, 4658, 4736, 5034], device="cuda")
+    for ci, start in enumerate(range(0, n, chunk)):
+        cnt = min(chunk, n - start)
+        r = npk.rank7_colex(start, cnt).to(torch.int64)
+        idx = torch.arange(start, start + cnt, device="cuda", dtype=torch.int64)
+        census = torch.bucketize(r, ts[1:9], right=True).bincount(minlength=9)
+        got = [int(r.sum()), int((r * (idx % 65521 + 1)).sum())] + census.tolist()
+        assert got == gold["chunks"][ci], ci
+        if ci in (0, 31, 63):
+            assert (r.cpu().numpy() == oracle.colex_range(start, cnt)[0]).all()
+
+
 def test_rank7_empty_and_ragged(torch_mod):
     torch = torch_mod
     assert npk.rank7(np.zeros((0, 7), dtype=np.uint8)).numel() == 0
