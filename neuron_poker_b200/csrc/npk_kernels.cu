@@ -95,12 +95,25 @@ __device__ __forceinline__ uint32_t eval_player(const SmemAddr& a, uint32_t tota
 // for the next trial: the outcome of a trial depends only on (seed, query, trial), not on how trials are partitioned.
 //
 // Random numbers: Philox4x32-10, counter = (trial_lo, trial_hi, query, block), key = seed.  Each 32-bit word serves two
-// draws by multiply-shift with remainder reuse: x*m -> (index, x'), x'*(m-1) -> index; bias < 2^-26 per draw.
+// draws by multiply-shift with remainder reuse: x*m -> (index, x'), x'*(m-1) -> index; the first draw of a word is
+// uniform to within 2^-26, the second to within 2^-20 (the remainder takes 2^32/m equally spaced values).
+// A 64-bit fraction serving six draws (one Philox block for D <= 12) was built and measured in round 1: the two extra
+// multiply-adds per draw cost as much as the half-pruned second block saves, so the 32-bit form stayed.
 // =====================================================================================================================
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 template <int NOPP, int NB>
 __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(const EquityParams p)
 {
-    constexpr int kTrialsPerIter = 1;   // 2 was measured on B200 (round 1): no gain, the kernel is pipe-bound not latency-bound
     constexpr int KNOWN = 5 - NB;
     constexpr int N = 50 - KNOWN;          // unseen cards
     constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
@@ -116,6 +129,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
     // per-warp: 64-word scratch (static deck order) + interleaved deck (N rows x 32 lanes)
     uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + N * 32);
     uint32_t* fy = scratch + 64 + lane;
+    const uint32_t fy_addr = smem_u32(fy);   // one 32-bit shared address: element j of this lane at fy_addr + 128*j
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
     const long long n_items = p.nq * chunks;
@@ -142,67 +156,57 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
         uint32_t wins = 0, ties = 0;
         unsigned long long wt_pack = 0;   // nine 7-bit win-type counters (<= 64 iterations per item)
 
-        // kTrialsPerIter independent trials per loop iteration: their Philox rounds and table gathers interleave in
-        // the instruction stream (more independent work per warp), only the deck shuffles stay strictly in order.
-        for (long long tb = t_begin; tb < t_end; tb += 32 * kTrialsPerIter) {
-            uint32_t dv[kTrialsPerIter][D > 0 ? D : 1];
-            bool active[kTrialsPerIter];
+        for (long long tb = t_begin; tb < t_end; tb += 32) {
+            const long long t_local = tb + lane;
+            const bool active = t_local < t_end;
+            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
+            uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
 #pragma unroll
-            for (int u = 0; u < kTrialsPerIter; u++) {
-                const long long t_local = tb + 32 * u + lane;
-                active[u] = t_local < t_end;
-                const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
-                uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
+            for (int b = 0; b < NBLK; b++)
+                philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, (uint32_t)b,
+                              p.seed_lo, p.seed_hi, &w[4 * b]);
+            uint32_t dv[D > 0 ? D : 1], slot[D > 0 ? D : 1];
+            uint32_t rem = 0;
 #pragma unroll
-                for (int b = 0; b < NBLK; b++)
-                    philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, (uint32_t)b,
-                                  p.seed_lo, p.seed_hi, &w[4 * b]);
-                uint32_t slot[D > 0 ? D : 1];
-                uint32_t rem = 0;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
-                    const uint32_t x = (k & 1) ? rem : w[k >> 1];
-                    // index = high word, remainder = low word of x * (N - k).  Written as mul.hi / mul.lo on purpose:
-                    // ptxas 12.9 miscompiled the 64-bit form for the last draw (whose low word is dead) into
-                    // lo32(x * 4 * (N - k)) -- an out-of-range shared address caught by the per-shape parity test.
-                    const uint32_t idx = __umulhi(x, (uint32_t)(N - k));
-                    rem = x * (uint32_t)(N - k);
-                    slot[k] = idx * 32;
-                    dv[u][k] = fy[idx * 32];
-                    fy[idx * 32] = fy[(N - 1 - k) * 32];
-                }
-#pragma unroll
-                for (int k = D - 1; k >= 0; k--) fy[slot[k]] = dv[u][k];
+            for (int k = 0; k < D; k++) {
+                const uint32_t x = (k & 1) ? rem : w[k >> 1];
+                // index = high word, remainder = low word of x * (N - k).  Written as mul.hi / mul.lo on purpose:
+                // ptxas 12.9 miscompiled the 64-bit form for the last draw (whose low word is dead) into
+                // lo32(x * 4 * (N - k)) -- an out-of-range shared address caught by the per-shape parity test.
+                const uint32_t idx = __umulhi(x, (uint32_t)(N - k));
+                rem = x * (uint32_t)(N - k);
+                slot[k] = fy_addr + idx * 128u;
+                dv[k] = lds_u32(slot[k]);
+                sts_u32(slot[k], lds_u32(fy_addr + (uint32_t)(N - 1 - k) * 128u));
             }
+#pragma unroll
+            for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[k]);
 
+            // board: descriptor sum, suit counters -> the one suit that can still flush, its rank mask
+            uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
 #pragma unroll
-            for (int u = 0; u < kTrialsPerIter; u++) {
-                // board: descriptor sum, suit counters -> the one suit that can still flush, its rank mask
-                uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
+            for (int k = 2 * NOPP; k < D; k++) { bsum += dv[k]; bcnt += suit_inc(dv[k]); }
+            const BoardFlush bf = board_flush(bcnt);
+            uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
 #pragma unroll
-                for (int k = 2 * NOPP; k < D; k++) { bsum += dv[u][k]; bcnt += suit_inc(dv[u][k]); }
-                const BoardFlush bf = board_flush(bcnt);
-                uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
-#pragma unroll
-                for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[u][k], bf.fsx);
+            for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[k], bf.fsx);
 
-                const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
-                uint32_t best = 0;
+            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
+            uint32_t best = 0;
 #pragma unroll
-                for (int o = 0; o < NOPP; o++) {
-                    const uint32_t d0 = dv[u][2 * o], d1 = dv[u][2 * o + 1];
-                    const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
-                    best = max(best, ov);
-                }
-                // a lone hero (NOPP == 0) is the best of one hand (reference: index 0 of a one-element list)
-                const bool win = active[u] && (NOPP == 0 || hv > best), tie = active[u] && NOPP > 0 && hv == best;
-                wins += win; ties += tie;
-                if (p.win_types && (win || tie)) {
-                    uint32_t ty = 0;
+            for (int o = 0; o < NOPP; o++) {
+                const uint32_t d0 = dv[2 * o], d1 = dv[2 * o + 1];
+                const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
+                best = max(best, ov);
+            }
+            // a lone hero (NOPP == 0) is the best of one hand (reference: index 0 of a one-element list)
+            const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
+            wins += win; ties += tie;
+            if (p.win_types && (win || tie)) {
+                uint32_t ty = 0;
 #pragma unroll
-                    for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
-                    wt_pack += 1ull << (7 * ty);
-                }
+                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                wt_pack += 1ull << (7 * ty);
             }
         }
 
