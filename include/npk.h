@@ -12,6 +12,8 @@
  *                       i.e. what get_equity (montecarlo_python.py:401-406) and the pybind11 export
  *                       pymontecarlo.montecarlo (tools/montecarlo_cpp/pymontecarlo.cpp:21-23) compute, batched
  *   npk_equity_host     the same, for HOST buffers: one blocking call = one (batch of) get_equity call(s)
+ *   npk_equity_ranges_* the same loop with an opponent range, a hero range and ghost cards
+ *                                                                 tools/montecarlo_python.py:24-112, :136-181, :206-208
  *   npk_rank7_batch     _calc_score ordering                      tools/hand_evaluator.py:27-119
  *   npk_showdown_batch  get_winner / eval_best_hand               tools/hand_evaluator.py:9-24 (used by gym_env/env.py:576-593)
  *   npk_enum_batch      no counterpart (the reference only samples); exact enumeration used for bit-exact checks
@@ -38,6 +40,7 @@ extern "C" {
 #define NPK_ERR_CUDA (-3)
 #define NPK_ERR_TABLES (-4)
 #define NPK_ERR_INVALID_CARDS (-5)   /* card id >= 52, duplicate cards, board with holes, players outside 1..10 */
+#define NPK_ERR_RANGE (-6)           /* a range that no remaining card combination can satisfy */
 
 /* dealing semantics */
 #define NPK_DEAL_UNIFORM 0   /* uniform without replacement = the C++ sibling's std::shuffle (Montecarlo.cpp:293-312)   */
@@ -99,6 +102,33 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
 int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
                     uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                     uint64_t* passes);
+
+/*
+ * Monte-Carlo equity with RANGES (run_montecarlo's opponent_range / set-typed player cards / ghost_cards).
+ * A starting-hand class is an unordered rank pair plus suitedness, numbered  suited hi*13+lo,  offsuit and pairs
+ * lo*13+hi  (rank indices in "23456789TJQKA", hi >= lo); a range is a 169-bit mask in three uint64 words (HOST memory).
+ *   opp_allowed   [3] host: classes every opponent's two cards must belong to
+ *   hero_allowed  [3] host or NULL: if given, the hero's cards are drawn from this range every trial and `hole` is
+ *                 ignored (may be NULL) -- the reference's "player_cards is a set" case
+ *   ghost         [Q,2] device or NULL: cards removed from the deck before dealing (0xFF = none)
+ * deal_mode NPK_DEAL_REFERENCE reproduces the reference dealer including the quirk that the range test looks at
+ * deck[i1], deck[i2] before popping (montecarlo_python.py:173-179); NPK_DEAL_UNIFORM is the unbiased counterpart
+ * (two distinct uniform cards, redrawn until the class is allowed).  passes [Q] counts the draw attempts of hero and
+ * opponents in both modes.  One generic kernel handles every mix of player counts and board sizes; the call is
+ * asynchronous unless NPK_FLAG_VALIDATE is set, in which case the stream is synchronised and a range no remaining
+ * hand can satisfy (one draw exceeded 65,536 attempts) is reported as NPK_ERR_RANGE.  Other arguments as above.
+ */
+int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                            int64_t Q, int64_t trials, const uint64_t* opp_allowed, const uint64_t* hero_allowed,
+                            uint64_t seed, int64_t trial_offset, int64_t query_offset, int deal_mode, uint32_t flags,
+                            uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
+                            void* stream);
+/* HOST buffers in and out, blocking, validated (NPK_ERR_INVALID_CARDS / NPK_ERR_RANGE): one run_montecarlo call with
+ * ranges, or a batch of them sharing the same ranges.  hole may be NULL when hero_allowed is given; ghost [Q,2] or NULL. */
+int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                           int64_t Q, int64_t trials, const uint64_t* opp_allowed, const uint64_t* hero_allowed,
+                           uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
+                           uint64_t* passes);
 
 /* rank ids of N 7-card hands */
 int npk_rank7_batch(const uint8_t* cards /*[N,7]*/, int64_t N, uint16_t* ranks /*[N]*/, void* stream);

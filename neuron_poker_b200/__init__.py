@@ -9,9 +9,9 @@ plus batched entry points on CUDA tensors (get_equity_batch, rank7, showdown, en
 All compute runs in libnpk.so's CUDA kernels; importing this package does not import torch.
 """
 from .cards import CARD_RANKS_ORIGINAL, SUITS_ORIGINAL, HAND_TYPES, card_id, card_str  # noqa: F401
-from .equity import (DEAL_REFERENCE, DEAL_UNIFORM, MonteCarlo, equity_counts, equity_counts_batch, get_equity,  # noqa: F401
-                     get_equity_batch, montecarlo, seed)
-from . import dist  # noqa: F401
+from .equity import (DEAL_REFERENCE, DEAL_UNIFORM, MonteCarlo, equity_counts, equity_counts_batch,  # noqa: F401
+                     equity_counts_ranges, get_equity, get_equity_batch, get_equity_ranges_batch, montecarlo, seed)
+from . import dist, ranges  # noqa: F401
 from .evaluator import (enumerate_equity, eval_best_hand, get_winner, host_rank7, host_tables, rank7, rank7_colex,  # noqa: F401
                         showdown)
 

@@ -14,7 +14,7 @@ NPK_DEAL_UNIFORM = 0
 NPK_DEAL_REFERENCE = 1
 NPK_FLAG_VALIDATE = 1
 ERRORS = {-1: "NPK_ERR_NOT_INITIALIZED", -2: "NPK_ERR_INVALID_ARGUMENT", -3: "NPK_ERR_CUDA", -4: "NPK_ERR_TABLES",
-          -5: "NPK_ERR_INVALID_CARDS"}
+          -5: "NPK_ERR_INVALID_CARDS", -6: "NPK_ERR_RANGE"}
 
 
 class NpkError(RuntimeError):
@@ -45,6 +45,10 @@ def lib():
                 L.npk_equity_batch.argtypes = [u8, u8, u8, i64, i64, i32, i32, ctypes.c_uint64, i64, i64, i32,
                                                ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
                 L.npk_equity_host.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, i32, u64, u64, u64, u64]
+                L.npk_equity_ranges_batch.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i64, i64, i32,
+                                                      ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
+                L.npk_equity_ranges_host.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i32, u64, u64,
+                                                     u64, u64]
                 L.npk_rank7_batch.argtypes = [u8, i64, u16, vp]
                 L.npk_rank7_colex.argtypes = [i64, i64, u16, vp]
                 L.npk_enum_batch.argtypes = [u8, u8, u8, i64, u64, u64, u64, vp]

@@ -79,8 +79,8 @@ int current_state(DeviceState** out)
 
 // ---- query classification (mixed player counts / board sizes) --------------------------------------------------------
 // workspace layout (bytes): [0,512) 64 work counters u64 | [512,768) 64 group counts u32 | [768,1024) 64 cursors u32
-//                           | [1024,1028) invalid-query count | [2048, 2048+4Q) qindex
-constexpr int kWsCounters = 0, kWsCounts = 512, kWsCursors = 768, kWsInvalid = 1024, kWsIndex = 2048;
+//                           | [1024,1028) invalid-query count | [1028,1032) range abort flag | [2048, 2048+4Q) qindex
+constexpr int kWsCounters = 0, kWsCounts = 512, kWsCursors = 768, kWsInvalid = 1024, kWsAbort = 1028, kWsIndex = 2048;
 constexpr int kGroups = 60;   // group = nopp * 6 + known, nopp 0..9, known 0..5
 
 __device__ __forceinline__ int classify_query(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
@@ -439,6 +439,156 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     std::memcpy(ties, st.h_out + Q, 8 * Q);
     if (win_types) std::memcpy(win_types, st.h_out + 2 * Q, 8 * 9 * Q);
     if (passes) std::memcpy(passes, st.h_out + 11 * Q, 8 * Q);
+    return NPK_OK;
+}
+
+// ---- ranges ------------------------------------------------------------------------------------------------------------
+__global__ void validate_ranges_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
+                                       const uint8_t* ghost, long long Q, uint8_t* ws)
+{
+    uint32_t* invalid = reinterpret_cast<uint32_t*>(ws + kWsInvalid);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
+        const int np = n_players[q];
+        unsigned long long mask = 0;
+        int bad = np < 1 || np > 10;
+        bool ended = false;
+        if (hole)
+            for (int i = 0; i < 2; i++) {
+                const int c = hole[2 * q + i];
+                if (c >= 52) bad = 1; else { bad |= (int)(mask >> c & 1ull); mask |= 1ull << c; }
+            }
+        for (int i = 0; i < 5; i++) {
+            const int c = board[5 * q + i];
+            if (c == 0xFF) { ended = true; continue; }
+            if (ended || c >= 52) { bad = 1; continue; }
+            bad |= (int)(mask >> c & 1ull);
+            mask |= 1ull << c;
+        }
+        if (ghost) {
+            // the reference pops ghost cards from the deck first (montecarlo_python.py:206-208): a board card equal to
+            // a ghost card then fails list.index (ValueError); a hero card equal to one is silently kept (:154-161)
+            const int g0 = ghost[2 * q], g1 = ghost[2 * q + 1];
+            if ((g0 == 0xFF) != (g1 == 0xFF)) bad = 1;
+            else if (g0 != 0xFF) {
+                if (g0 >= 52 || g1 >= 52 || g0 == g1) bad = 1;
+                else bad |= (int)((mask >> g0 | mask >> g1) & 1ull);
+            }
+        }
+        if (bad) atomicAdd(invalid, 1u);
+    }
+}
+
+int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                            int64_t Q, int64_t trials, const uint64_t* opp_allowed, const uint64_t* hero_allowed,
+                            uint64_t seed, int64_t trial_offset, int64_t query_offset, int deal_mode, uint32_t flags,
+                            uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
+                            void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q < 0 || trials < 0 || trial_offset < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (Q == 0 || trials == 0) return NPK_OK;
+    if (Q > 0x7fffffffLL) return fail(NPK_ERR_INVALID_ARGUMENT, "at most 2^31-1 queries per call");
+    if ((!hole && !hero_allowed) || !board || !n_players || !wins_strict || !ties || !workspace || !opp_allowed)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+    const uint64_t top = (1ull << (169 - 128)) - 1ull;
+    if (!(opp_allowed[0] | opp_allowed[1] | (opp_allowed[2] & top)))
+        return fail(NPK_ERR_RANGE, "the opponent range is empty (the reference would never finish a draw)");
+    if (hero_allowed && !(hero_allowed[0] | hero_allowed[1] | (hero_allowed[2] & top)))
+        return fail(NPK_ERR_RANGE, "the hero range is empty (the reference would never finish a draw)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    cudaError_t e = cudaMemsetAsync(ws, 0, kWsIndex, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+
+    npk::EquityParams p{};
+    p.tables = ds->t;
+    p.hole = hero_allowed ? nullptr : hole; p.board = board; p.n_players = n_players; p.ghost = ghost;
+    p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count);
+    p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
+    p.ties = reinterpret_cast<unsigned long long*>(ties);
+    p.win_types = reinterpret_cast<unsigned long long*>(win_types);
+    p.passes = reinterpret_cast<unsigned long long*>(passes);
+    p.qindex = nullptr; p.nq = Q;
+    p.work_counter = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+    p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);
+    for (int i = 0; i < 3; i++) {
+        const uint64_t o = i == 2 ? opp_allowed[i] & top : opp_allowed[i];
+        const uint64_t h = hero_allowed ? (i == 2 ? hero_allowed[i] & top : hero_allowed[i]) : 0;
+        p.opp_mask[2 * i] = (uint32_t)o; p.opp_mask[2 * i + 1] = (uint32_t)(o >> 32);
+        p.hero_mask[2 * i] = (uint32_t)h; p.hero_mask[2 * i + 1] = (uint32_t)(h >> 32);
+    }
+    p.hero_range = hero_allowed ? 1u : 0u;
+
+    const bool validate = (flags & NPK_FLAG_VALIDATE) != 0;
+    if (validate) {
+        const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
+        validate_ranges_kernel<<<cg, 256, 0, s>>>(p.hole, board, n_players, ghost, Q, ws);
+        uint32_t bad = 0;
+        e = cudaMemcpyAsync(&bad, ws + kWsInvalid, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail(e, "query validation");
+        if (bad) return fail(NPK_ERR_INVALID_CARDS, std::to_string(bad) + " invalid quer" + (bad == 1 ? "y" : "ies") +
+                             " (card id >= 52, duplicate cards, gap in the board, ghost card on the board or in the "
+                             "hand, or players outside 1..10)");
+    }
+    const long long chunks = (trials + p.chunk - 1) / p.chunk;
+    e = npk::launch_equity_ranges(deal_mode, p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
+    if (e != cudaSuccess) return cuda_fail(e, "equity_ranges_kernel launch");
+    if (validate) {
+        uint32_t aborted = 0;
+        e = cudaMemcpyAsync(&aborted, ws + kWsAbort, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return cuda_fail(e, "equity_ranges_kernel");
+        if (aborted) return fail(NPK_ERR_RANGE, "a draw needed more than 65536 attempts: no remaining hand satisfies the "
+                                                "range (the reference would loop forever); the counters are incomplete");
+    }
+    return NPK_OK;
+}
+
+int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                           int64_t Q, int64_t trials, const uint64_t* opp_allowed, const uint64_t* hero_allowed,
+                           uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
+                           uint64_t* passes)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
+    if ((!hole && !hero_allowed) || !board || !n_players || !wins_strict || !ties)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    // device staging private to this call (ranges are the rare path; the plain path keeps its pinned staging)
+    uint8_t* d_in = nullptr;
+    uint64_t* d_out = nullptr;
+    void* d_ws = nullptr;
+    cudaError_t e;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws); };
+    if ((e = cudaMalloc(&d_in, 10 * Q)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&d_out, 8 * 12 * Q)) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
+    if ((e = cudaMalloc(&d_ws, npk_equity_workspace_bytes(Q))) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
+    std::vector<uint8_t> h_in(10 * (size_t)Q, 0xFF);
+    if (hole) std::memcpy(h_in.data(), hole, 2 * Q);
+    std::memcpy(h_in.data() + 2 * Q, board, 5 * Q);
+    std::memcpy(h_in.data() + 7 * Q, n_players, Q);
+    if (ghost) std::memcpy(h_in.data() + 8 * Q, ghost, 2 * Q);
+    if ((e = cudaMemcpy(d_in, h_in.data(), 10 * Q, cudaMemcpyHostToDevice)) != cudaSuccess) { cleanup(); return cuda_fail(e, "H2D"); }
+    if ((e = cudaMemset(d_out, 0, 8 * 12 * Q)) != cudaSuccess) { cleanup(); return cuda_fail(e, "memset"); }
+    rc = npk_equity_ranges_batch(hole ? d_in : nullptr, d_in + 2 * Q, d_in + 7 * Q, ghost ? d_in + 8 * Q : nullptr, Q, trials,
+                                 opp_allowed, hero_allowed, seed, 0, 0, deal_mode, NPK_FLAG_VALIDATE, d_out, d_out + Q,
+                                 win_types ? d_out + 2 * Q : nullptr, passes ? d_out + 11 * Q : nullptr, d_ws, nullptr);
+    if (rc) { cleanup(); return rc; }
+    std::vector<uint64_t> h_out(12 * (size_t)Q);
+    if ((e = cudaMemcpy(h_out.data(), d_out, 8 * 12 * Q, cudaMemcpyDeviceToHost)) != cudaSuccess) { cleanup(); return cuda_fail(e, "D2H"); }
+    cleanup();
+    std::memcpy(wins_strict, h_out.data(), 8 * Q);
+    std::memcpy(ties, h_out.data() + Q, 8 * Q);
+    if (win_types) std::memcpy(win_types, h_out.data() + 2 * Q, 8 * 9 * Q);
+    if (passes) std::memcpy(passes, h_out.data() + 11 * Q, 8 * Q);
     return NPK_OK;
 }
 

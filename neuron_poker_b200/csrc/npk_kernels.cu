@@ -374,6 +374,167 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
 }
 
 // =====================================================================================================================
+// K1'': dealing with ranges.  Opponents -- and optionally the hero -- hold only hands whose starting-hand
+// class is in a 169-bit mask; ghost cards are removed from the deck first.  Reference: montecarlo_python.py:24-34
+// (class of two cards), :136-148 (hero drawn from a range), :165-181 (opponent range test), :206-208 (ghost cards).
+//   REFERENCE (MODE 1): i1 = hi32(w*n), i2 = hi32(lo32(w*n)*(n-1)); retry while i1 == i2 or the class of
+//       (deck[i1], deck[i2]) -- both read BEFORE anything is popped (:173-174) -- is not allowed.  A hero keeps exactly
+//       those two cards (:146-148); an opponent receives deck.pop(i1) and then deck.pop(i2) from the SHORTENED list
+//       (:178-179), so for i2 >= i1 the tested and the dealt second card differ (reference quirk, kept).
+//       Board card j = hi32(w*(n-1)) (:188).  With a full mask and a fixed hero this is equity_reference_kernel.
+//   UNIFORM (MODE 0): c1 = deck[i1], c2 = (deck without c1)[i2], retry while their class is not allowed; board uniform.
+// One Philox word per attempt, blocks from 0x80000000 (REFERENCE) / 0xC0000000 (UNIFORM).  A draw that needs more than
+// kMaxRangeAttempts attempts raises p.abort_flag; every warp then stops at its next trial (the host reports the error).
+// =====================================================================================================================
+__device__ __forceinline__ bool class_allowed(const uint32_t (&mask)[6], int c1, int c2)
+{
+    const int r1 = c1 >> 2, r2 = c2 >> 2, hi = max(r1, r2), lo = min(r1, r2);
+    const int k = ((c1 ^ c2) & 3) == 0 ? hi * 13 + lo : lo * 13 + hi;
+    return (mask[k >> 5] >> (k & 31)) & 1u;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const EquityParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
+    const int lane = threadIdx.x & 31;
+
+    const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
+    const long long n_items = p.nq * chunks;
+
+    for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
+        const long long qslot = item / chunks, ci = item - qslot * chunks;
+        const long long q = p.qindex ? p.qindex[qslot] : qslot;
+        int known = 0;
+        for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
+        const int nopp = (int)p.n_players[q] - 1;
+
+        // static part of the query: the known board, the cards nobody can receive
+        uint64_t taken = 0;
+        uint32_t board_sum = 0, board_lo = 0, board_hi = 0, board_cnt = 0x5555u;
+        for (int i = 0; i < known; i++) {
+            const uint8_t c = p.board[5 * q + i];
+            const uint32_t d = p.tables.desc[c];
+            uint32_t l, h;
+            card_bits(d, l, h);
+            board_sum += d; board_lo |= l; board_hi |= h; board_cnt += suit_inc(d);
+            taken |= 1ull << c;
+        }
+        if (p.ghost)
+            for (int i = 0; i < 2; i++) { const uint8_t c = p.ghost[2 * q + i]; if (c < 52) taken |= 1ull << c; }
+        int h0 = 0, h1 = 0;
+        if (!p.hero_range) { h0 = p.hole[2 * q]; h1 = p.hole[2 * q + 1]; taken |= (1ull << h0) | (1ull << h1); }
+        const uint64_t avail0 = ~taken & ((1ull << 52) - 1ull);
+        const int n0 = __popcll(avail0);
+
+        const long long t_begin = ci * p.chunk;
+        const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
+        uint32_t wins = 0, ties = 0;
+        unsigned long long passes = 0;
+        unsigned long long wt_pack = 0;
+
+        for (long long tb = t_begin; tb < t_end; tb += 32) {
+            if (*reinterpret_cast<volatile uint32_t*>(p.abort_flag)) break;
+            const long long t_local = tb + lane;
+            bool active = t_local < t_end;
+            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
+            WordStream rs;
+            rs.c0 = (uint32_t)trial; rs.c1 = (uint32_t)(trial >> 32); rs.c2 = (uint32_t)q + p.query_offset;
+            rs.k0 = p.seed_lo; rs.k1 = p.seed_hi; rs.blk = MODE == 1 ? 0x80000000u : 0xC0000000u; rs.have = 0;
+
+            uint64_t avail = avail0;
+            int n = n0;
+            uint32_t hd0 = 0, hd1 = 0, best = 0;
+            uint32_t oc1[9], oc2[9];
+            if (active) {
+                // hand 0 = the hero when drawn from a range, hands 1.. = the opponents
+                for (int o = p.hero_range ? -1 : 0; o < nopp && active; o++) {
+                    const bool is_hero = o < 0;
+                    int c1 = 0, c2 = 0;
+                    uint32_t tries = 0;
+                    for (;;) {
+                        if (++tries > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); active = false; break; }
+                        passes++;
+                        const uint64_t prod = (uint64_t)rs.next() * (uint32_t)n;
+                        const uint32_t i1 = (uint32_t)(prod >> 32);
+                        const uint32_t i2 = __umulhi((uint32_t)prod, (uint32_t)(n - 1));
+                        if (MODE == 1 && i1 == i2) continue;
+                        c1 = select_bit(avail, (int)i1);
+                        if (MODE == 1) {
+                            const int ct = select_bit(avail, (int)i2);           // tested BEFORE popping c1
+                            if (!(is_hero ? class_allowed(p.hero_mask, c1, ct) : class_allowed(p.opp_mask, c1, ct))) continue;
+                            c2 = is_hero ? ct : select_bit(avail & ~(1ull << c1), (int)i2);
+                        } else {
+                            c2 = select_bit(avail & ~(1ull << c1), (int)i2);
+                            if (!(is_hero ? class_allowed(p.hero_mask, c1, c2) : class_allowed(p.opp_mask, c1, c2))) continue;
+                        }
+                        break;
+                    }
+                    avail &= ~((1ull << c1) | (1ull << c2));
+                    n -= 2;
+                    if (is_hero) { h0 = c1; h1 = c2; }
+                    else { oc1[o] = p.tables.desc[c1]; oc2[o] = p.tables.desc[c2]; }
+                }
+            }
+            hd0 = p.tables.desc[h0]; hd1 = p.tables.desc[h1];
+            uint32_t bsum = board_sum, bcnt = board_cnt;
+            uint32_t bd[5];
+            int nbd = 0;
+            if (active) {
+                for (int k = known; k < 5; k++) {
+                    const uint32_t j = __umulhi(rs.next(), (uint32_t)(MODE == 1 ? n - 1 : n));
+                    const int c = select_bit(avail, (int)j);
+                    avail &= ~(1ull << c);
+                    n--;
+                    const uint32_t d = p.tables.desc[c];
+                    bd[nbd++] = d;
+                    bsum += d; bcnt += suit_inc(d);
+                }
+            }
+            const BoardFlush bf = board_flush(bcnt);
+            uint32_t bfield = prmt(board_lo, board_hi, bf.sel);
+            for (int k = 0; k < nbd; k++) bfield |= flush_bit(bd[k], bf.fsx);
+            const uint32_t hv = eval_player(st, bsum + hd0 + hd1, bfield | flush_bit(hd0, bf.fsx) | flush_bit(hd1, bf.fsx), bf.thr);
+            if (active)
+                for (int o = 0; o < nopp; o++)
+                    best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
+                                                 bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
+            const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
+            wins += win; ties += tie;
+            if (p.win_types && (win || tie)) {
+                uint32_t ty = 0;
+#pragma unroll
+                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                wt_pack += 1ull << (7 * ty);
+            }
+        }
+        wins = __reduce_add_sync(0xffffffffu, wins);
+        ties = __reduce_add_sync(0xffffffffu, ties);
+        if (lane == 0) {
+            atomicAdd(&p.wins[q], (unsigned long long)wins);
+            atomicAdd(&p.ties[q], (unsigned long long)ties);
+        }
+        if (p.passes) {
+            // 64-bit warp sum in three 21-bit slices (a lane makes at most 64 * 10 * 65536 < 2^26 attempts per item)
+            unsigned long long tot = 0;
+#pragma unroll
+            for (int sft = 0; sft < 63; sft += 21)
+                tot += (unsigned long long)__reduce_add_sync(0xffffffffu, (uint32_t)(passes >> sft) & 0x1fffffu) << sft;
+            if (lane == 0) atomicAdd(&p.passes[q], tot);
+        }
+        if (p.win_types) {
+#pragma unroll
+            for (int i = 0; i < 9; i++) {
+                uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)(wt_pack >> (7 * i)) & 127u);
+                if (lane == 0 && c) atomicAdd(&p.win_types[9 * q + i], (unsigned long long)c);
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
 // K2: rank ids of 7-card hands
 // =====================================================================================================================
 __global__ void __launch_bounds__(kAuxThreads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
@@ -697,6 +858,16 @@ cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_
     cudaError_t e = cudaFuncSetAttribute(equity_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     equity_reference_kernel<<<grid, kRefThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s)
+{
+    size_t smem = aux_smem(p.tables);
+    auto k = deal_mode == 1 ? equity_ranges_kernel<1> : equity_ranges_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kRefThreads, smem, s>>>(p);
     return cudaGetLastError();
 }
 

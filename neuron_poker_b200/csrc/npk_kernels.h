@@ -28,7 +28,15 @@ struct EquityParams {
     unsigned long long* ties;     // [Q] hero ties for best
     unsigned long long* win_types;// [Q,9] or null: hand type of the hero whenever he wins or ties
     unsigned long long* passes;   // [Q] or null: reference-mode draw attempts (montecarlo_python.py:167)
+    // ---- ranges (equity_ranges_kernel only) ----
+    uint32_t opp_mask[6];         // 169-bit mask of the starting-hand classes an opponent may hold
+    uint32_t hero_mask[6];        // the same for the hero when hero_range != 0
+    uint32_t hero_range;          // 1: the hero is drawn from hero_mask every trial (`hole` is not read)
+    const uint8_t* ghost;         // [Q,2] cards removed from the deck before dealing (0xFF = none), or null
+    uint32_t* abort_flag;         // raised when one draw needs more than kMaxRangeAttempts attempts
 };
+
+constexpr uint32_t kMaxRangeAttempts = 1u << 16;
 
 struct EnumParams {
     DeviceTables tables;
@@ -45,6 +53,7 @@ size_t aux_smem(const DeviceTables& t);
 cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
                                   cudaStream_t s);
 cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s);
+cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_enum(const EnumParams& p, int grid, cudaStream_t s);

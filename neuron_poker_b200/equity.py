@@ -21,8 +21,8 @@ from collections import Counter
 
 import numpy as np
 
-from . import _lib
-from .cards import HAND_TYPES, NO_CARD, encode_query
+from . import _lib, ranges
+from .cards import HAND_TYPES, NO_CARD, card_ids, encode_query
 
 DEAL_UNIFORM = _lib.NPK_DEAL_UNIFORM
 DEAL_REFERENCE = _lib.NPK_DEAL_REFERENCE
@@ -125,22 +125,92 @@ def montecarlo(my_cards, cards_on_table, number_of_players, iterations):
     return (r["wins"] + r["ties"]) / iterations
 
 
+def _u64(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def equity_counts_ranges(player_cards, table_cards, players, runs, opponent_range=1, ghost_cards='',
+                         deal_mode="reference", seed_value=None):
+    """One run_montecarlo call with ranges through npk_equity_ranges_host (blocking).
+
+    player_cards: two card strings, or a SET of class spellings ('AKO', 'AA', ...): the hero is then drawn from that
+    range every trial (montecarlo_python.py:136-148).  opponent_range: a fraction of the reference's preflop ranking
+    (:36-112) or a set of class spellings (:194-199).  ghost_cards: '' or two cards removed from the deck (:206-208).
+    Returns dict(wins, ties, runs, win_types[9], passes)."""
+    players, runs = int(players), int(runs)
+    if players < 1:
+        raise IndexError("list index out of range")
+    if players > 10:
+        raise ValueError("at most 10 players")
+    hero_is_range = isinstance(player_cards, (set, frozenset))       # reference: `type(player_cards) == set` (:136)
+    board = card_ids(table_cards)
+    if len(board) > 5:
+        raise ValueError("table_cards holds more than five cards")
+    ghost = card_ids(ghost_cards) if ghost_cards not in ('', None) else []
+    if ghost and len(ghost) != 2:
+        raise ValueError("ghost_cards must be '' or two cards")
+    hole = None
+    if not hero_is_range:
+        hole = card_ids(player_cards)
+        if len(hole) != 2:
+            raise ValueError("player_cards must hold exactly two cards, got %d" % len(hole))
+    opp_mask = ranges.opponent_mask(opponent_range)
+    hero_mask = ranges.mask_from_classes(player_cards) if hero_is_range else None
+    L = _lib.ensure_init(_device())
+    hole_a = np.array(hole, dtype=np.uint8) if hole is not None else None
+    board_a = np.array(board + [NO_CARD] * (5 - len(board)), dtype=np.uint8)
+    ghost_a = np.array(ghost, dtype=np.uint8) if ghost else None
+    npl = np.array([players], dtype=np.uint8)
+    out_w, out_t = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+    out_ty, out_p = np.zeros(9, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
+    s = _next_seed() if seed_value is None else int(seed_value)
+    _lib.check(L.npk_equity_ranges_host(_u8(hole_a) if hole_a is not None else None, _u8(board_a), _u8(npl),
+                                        _u8(ghost_a) if ghost_a is not None else None, 1, runs, _u64(opp_mask),
+                                        _u64(hero_mask) if hero_mask is not None else None,
+                                        ctypes.c_uint64(s & (2**64 - 1)), _DEAL[deal_mode], _u8(out_w), _u8(out_t),
+                                        _u8(out_ty), _u8(out_p)))
+    return {"wins": int(out_w[0]), "ties": int(out_t[0]), "runs": runs, "win_types": [int(x) for x in out_ty],
+            "passes": int(out_p[0])}
+
+
 class MonteCarlo(object):
-    """Mirror of tools/montecarlo_python.py::MonteCarlo for the path get_equity uses (opponent_range=1, no ghost cards)."""
+    """Mirror of tools/montecarlo_python.py::MonteCarlo: the get_equity path (opponent_range=1) and the range / hero-range /
+    ghost-card variants of run_montecarlo."""
 
     def create_card_deck(self):
         from .cards import DECK
         return list(DECK)
 
+    def get_two_short_notation(self, input_cards, add_O_to_pairs=False):
+        """montecarlo_python.py:24-34: both spellings of the starting-hand class of two cards."""
+        card1, card2 = input_cards[0][0], input_cards[1][0]
+        suited_str = 'S' if input_cards[0][1] == input_cards[1][1] else 'O'
+        if card1 == card2:
+            suited_str = "O" if add_O_to_pairs else ''
+        return card1 + card2 + suited_str, card2 + card1 + suited_str
+
+    def get_opponent_allowed_cards_list(self, opponent_ranges):
+        """montecarlo_python.py:36-112: the top int(169 * range) classes of the reference's preflop ranking."""
+        return ranges.allowed_classes(opponent_ranges)
+
     def run_montecarlo(self, original_player_card_list, original_table_card_list, player_amount, ui, maxRuns,
                        timeout, ghost_cards, opponent_range=1):
-        """montecarlo_python.py:191-252.  `ui` and `timeout` are accepted and ignored (every run is executed)."""
-        if ghost_cards != '' or isinstance(opponent_range, set) or float(opponent_range) != 1.0:
-            raise NotImplementedError("opponent ranges / ghost cards are outside this path (SURVEY 8f-2)")
-        if len(original_player_card_list) != 1 or isinstance(original_player_card_list[0], set):
-            raise NotImplementedError("exactly one known hand (the hero) is supported")
-        r = equity_counts(original_player_card_list[0], original_table_card_list, player_amount, maxRuns,
-                          deal_mode="reference", win_types=True, passes=True)
+        """montecarlo_python.py:191-252.  `ui` and `timeout` are accepted and ignored (every run is executed).
+        The plain case (opponent_range=1, a fixed hero, no ghost cards) runs equity_reference_kernel; anything else runs
+        the range kernel.  A range no remaining hand can satisfy raises NpkError instead of looping forever."""
+        if len(original_player_card_list) != 1:
+            raise NotImplementedError("exactly one known hand or hero range is supported (the reference's collusion "
+                                      "case of several known hands is not used by any caller)")
+        hero = original_player_card_list[0]
+        plain = (ghost_cards == '' and not isinstance(opponent_range, (set, frozenset)) and
+                 not isinstance(hero, (set, frozenset)) and
+                 len(ranges.allowed_classes(opponent_range)) == ranges.N_CLASSES)
+        if plain:
+            r = equity_counts(hero, original_table_card_list, player_amount, maxRuns, deal_mode="reference",
+                              win_types=True, passes=True)
+        else:
+            r = equity_counts_ranges(hero, original_table_card_list, player_amount, maxRuns, opponent_range=opponent_range,
+                                     ghost_cards=ghost_cards, deal_mode="reference")
         runs = r["runs"]
         self.equity = (r["wins"] + r["ties"]) / runs
         self.winnerCardTypeList = Counter({HAND_TYPES[i]: c / runs for i, c in enumerate(r["win_types"]) if c})
@@ -151,6 +221,46 @@ class MonteCarlo(object):
 
 
 # ---- batched API on device tensors -----------------------------------------------------------------------------------
+def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, hero_range=None, ghost=None, seed_value=0,
+                            deal_mode="reference", trial_offset=0, query_offset=0, device=None, validate=True,
+                            win_types=False, passes=False, out=None):
+    """Batched Monte-Carlo counts with ranges (asynchronous on the current torch stream unless validate=True).
+
+    opponent_range: fraction or set of class spellings shared by every query; hero_range: None (fixed `hole` [Q,2]) or a
+    set of class spellings (the hero is drawn from it every trial, `hole` may be None); ghost: None or [Q,2] uint8
+    (0xFF = none).  Returns dict of int64 CUDA tensors like get_equity_batch."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    board = _as_cuda_u8(board, dev, (5,))
+    n_players = _as_cuda_u8(n_players, dev, ())
+    Q = board.shape[0]
+    hole = None if hero_range is not None else _as_cuda_u8(hole, dev, (2,))
+    ghost = None if ghost is None else _as_cuda_u8(ghost, dev, (2,))
+    opp_mask = ranges.opponent_mask(opponent_range)
+    hero_mask = None if hero_range is None else ranges.mask_from_classes(hero_range)
+    L = _lib.ensure_init(dev.index if dev.index is not None else 0)
+    with torch.cuda.device(dev):
+        out = {} if out is None else out
+        for name, shape, want in (("wins", (Q,), True), ("ties", (Q,), True), ("win_types", (Q, 9), win_types),
+                                  ("passes", (Q,), passes)):
+            if want and name not in out:
+                out[name] = torch.zeros(shape, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(L.npk_equity_workspace_bytes(Q)), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.npk_equity_ranges_batch(hole.data_ptr() if hole is not None else None, board.data_ptr(),
+                                             n_players.data_ptr(), ghost.data_ptr() if ghost is not None else None, Q,
+                                             int(trials), _u64(opp_mask), _u64(hero_mask) if hero_mask is not None else None,
+                                             ctypes.c_uint64(int(seed_value) & (2**64 - 1)), int(trial_offset),
+                                             int(query_offset), _DEAL[deal_mode],
+                                             _lib.NPK_FLAG_VALIDATE if validate else 0, out["wins"].data_ptr(),
+                                             out["ties"].data_ptr(), out["win_types"].data_ptr() if win_types else None,
+                                             out["passes"].data_ptr() if passes else None, ws.data_ptr(), stream))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    out["trials"] = int(trials)
+    return out
+
+
+
 def _as_cuda_u8(x, device, shape_tail):
     import torch
     if not isinstance(x, torch.Tensor):

@@ -400,6 +400,157 @@ int oracle_mc_reference(const uint8_t *hero, const uint8_t *board, int nboard, i
 }
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Ranges (reference tools/montecarlo_python.py:24-34 get_two_short_notation, :36-112 allowed list, :136-148 hero range,
+ * :165-181 opponent range test, :206-208 ghost cards).
+ * A starting-hand class is an unordered rank pair plus suitedness; the reference spells it rank chars + 'S' / 'O' / ''
+ * (pairs) and tests both spellings, so membership only depends on the class.  Class number used by every checker and
+ * by libnpk:  suited hi*13+lo,  offsuit and pairs lo*13+hi  (hi >= lo rank indices 0..12)  -> 169-bit masks uint64[3].
+ * ---------------------------------------------------------------------------------------------------------------- */
+int oracle_hand_class(int c1, int c2)
+{
+    int r1 = c1 >> 2, r2 = c2 >> 2, hi = r1 > r2 ? r1 : r2, lo = r1 > r2 ? r2 : r1;
+    return ((c1 & 3) == (c2 & 3)) ? hi * 13 + lo : lo * 13 + hi;
+}
+
+static int class_allowed(const uint64_t *mask, int c1, int c2)
+{
+    int k = oracle_hand_class(c1, c2);
+    return (int)(mask[k >> 6] >> (k & 63) & 1u);
+}
+
+#define ORACLE_MAX_ATTEMPTS 100000000LL   /* the reference would spin forever on an unsatisfiable range */
+
+/* MonteCarlo.run_montecarlo with an opponent range, optionally a hero RANGE (player_card_list[0] is a set, :136-148)
+ * and ghost cards (:206-208).  REFERENCE dealing, bit-exact under np.random.seed(seed).  Quirks kept:
+ *   - the range test looks at deck[i1], deck[i2] BEFORE anything is popped (:173-174) while the opponent receives
+ *     deck.pop(i1) and then deck.pop(i2) from the shortened list (:178-179): for i2 >= i1 the tested second card and
+ *     the dealt one differ;
+ *   - a hero drawn from a range keeps exactly the tested cards (:146-148) and is removed by value (:154-161).
+ * out layout as oracle_mc_reference.  Returns -3 when a draw exceeds ORACLE_MAX_ATTEMPTS. */
+int oracle_mc_reference_ranges(const uint8_t *hero, const uint64_t *hero_mask, const uint8_t *board, int nboard,
+                               int players, int64_t runs, uint32_t seed, const uint64_t *opp_mask, const uint8_t *ghost,
+                               int64_t *out)
+{
+    oracle_mt_t rng;
+    oracle_mt_seed(&rng, seed);
+    oracle_build_classes();
+    int64_t wins = 0, passes = 0, types[9] = {0};
+    if (players < 1) return -1;
+    uint8_t original[52]; int n0 = 52;
+    for (int i = 0; i < 52; i++) original[i] = (uint8_t)i;
+    if (ghost) {                                                 /* :206-208 */
+        for (int k = 0; k < 2; k++) {
+            int ix = list_index(original, n0, ghost[k]);
+            if (ix < 0) return -2;
+            list_pop(original, &n0, ix);
+        }
+    }
+    for (int64_t m = 0; m < runs; m++) {
+        uint8_t deck[52]; int n = n0;
+        memcpy(deck, original, 52);
+        uint8_t hole[10][2]; uint8_t table[5]; int nt = 0;
+        for (int i = 0; i < nboard; i++) {
+            int ix = list_index(deck, n, board[i]);
+            if (ix < 0) return -2;
+            table[nt++] = (uint8_t)list_pop(deck, &n, ix);
+        }
+        if (hero_mask) {                                         /* :136-148 */
+            int64_t i1, i2, tries = 0;
+            for (;;) {
+                passes++;
+                if (++tries > ORACLE_MAX_ATTEMPTS) return -3;
+                i1 = oracle_randint(&rng, 0, n);
+                i2 = oracle_randint(&rng, 0, n - 1);
+                if (i1 != i2 && class_allowed(hero_mask, deck[i1], deck[i2])) break;
+            }
+            hole[0][0] = deck[i1]; hole[0][1] = deck[i2];
+        } else {
+            hole[0][0] = hero[0]; hole[0][1] = hero[1];
+        }
+        for (int k = 0; k < 2; k++) {
+            int ix = list_index(deck, n, hole[0][k]);
+            if (ix >= 0) list_pop(deck, &n, ix);
+        }
+        for (int p = 1; p < players; p++) {                      /* :165-181 */
+            int64_t i1, i2, tries = 0;
+            for (;;) {
+                passes++;
+                if (++tries > ORACLE_MAX_ATTEMPTS) return -3;
+                i1 = oracle_randint(&rng, 0, n);
+                i2 = oracle_randint(&rng, 0, n - 1);
+                if (i1 != i2 && class_allowed(opp_mask, deck[i1], deck[i2])) break;
+            }
+            hole[p][0] = (uint8_t)list_pop(deck, &n, (int)i1);
+            hole[p][1] = (uint8_t)list_pop(deck, &n, (int)i2);
+        }
+        while (nt < 5)
+            table[nt++] = (uint8_t)list_pop(deck, &n, (int)oracle_randint(&rng, 0, n - 1));
+        int wt;
+        int winner = oracle_get_winner(&hole[0][0], players, table, &wt);
+        if (winner == 0) { wins++; types[wt]++; }
+    }
+    out[0] = wins; out[1] = passes;
+    for (int i = 0; i < 9; i++) out[2 + i] = types[i];
+    out[11] = oracle_randint(&rng, 0, 1000000);
+    return 0;
+}
+
+/* The unbiased counterpart used to check libnpk's UNIFORM mode with ranges (the C++ sibling has no ranges): hero (if
+ * drawn from a range) and every opponent receive two distinct cards drawn uniformly from the remaining deck, redrawn
+ * until their class is allowed; the board is uniform.  out[0]=wins_strict out[1]=ties out[2]=attempts. */
+int oracle_mc_uniform_ranges(const uint8_t *hero, const uint64_t *hero_mask, const uint8_t *board, int nboard,
+                             int players, int64_t runs, uint32_t seed, const uint64_t *opp_mask, const uint8_t *ghost,
+                             int64_t *out)
+{
+    oracle_mt_t rng;
+    oracle_mt_seed(&rng, seed);
+    oracle_build_classes();
+    int64_t wins = 0, ties = 0, attempts = 0;
+    for (int64_t m = 0; m < runs; m++) {
+        uint8_t deck[52]; int n = 0;
+        for (int c = 0; c < 52; c++) {
+            int known = 0;
+            if (!hero_mask) known |= (c == hero[0] || c == hero[1]);
+            if (ghost) known |= (c == ghost[0] || c == ghost[1]);
+            for (int i = 0; i < nboard; i++) known |= (c == board[i]);
+            if (!known) deck[n++] = (uint8_t)c;
+        }
+        uint8_t hole[10][2];
+        int first = hero_mask ? 0 : 1;
+        if (!hero_mask) { hole[0][0] = hero[0]; hole[0][1] = hero[1]; }
+        for (int p = first; p < players; p++) {
+            const uint64_t *mk = p == 0 ? hero_mask : opp_mask;
+            int64_t tries = 0;
+            int i1, i2;
+            for (;;) {
+                attempts++;
+                if (++tries > ORACLE_MAX_ATTEMPTS) return -3;
+                i1 = (int)oracle_randint(&rng, 0, n);
+                i2 = (int)oracle_randint(&rng, 0, n - 1);
+                if (i2 >= i1) i2++;
+                if (class_allowed(mk, deck[i1], deck[i2])) break;
+            }
+            hole[p][0] = deck[i1]; hole[p][1] = deck[i2];
+            int a = i1 > i2 ? i1 : i2, b = i1 > i2 ? i2 : i1;
+            list_pop(deck, &n, a); list_pop(deck, &n, b);
+        }
+        uint8_t table[5]; int nt = 0;
+        for (int i = 0; i < nboard; i++) table[nt++] = board[i];
+        while (nt < 5) table[nt++] = (uint8_t)list_pop(deck, &n, (int)oracle_randint(&rng, 0, n));
+        uint8_t h7[7] = {hole[0][0], hole[0][1], table[0], table[1], table[2], table[3], table[4]};
+        int hv = oracle_rank7(h7), best = -1;
+        for (int p = 1; p < players; p++) {
+            h7[0] = hole[p][0]; h7[1] = hole[p][1];
+            int v = oracle_rank7(h7);
+            if (v > best) best = v;
+        }
+        if (hv > best) wins++; else if (hv == best) ties++;
+    }
+    out[0] = wins; out[1] = ties; out[2] = attempts;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Uniform dealing (the C++ sibling's semantics, tools/montecarlo_cpp/Montecarlo.cpp:240-259, 293-312: shuffle the
  * remaining cards, deal consecutively to opponents then board; ties count as wins).  The sibling seeds a fresh
  * mt19937_64 from std::random_device every trial, so no stream can be matched -- statistical parity only; this port

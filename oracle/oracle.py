@@ -53,6 +53,11 @@ def lib():
         L.oracle_get_winner.argtypes = [u8p, ctypes.c_int, u8p, ctypes.POINTER(ctypes.c_int)]
         for name in ("oracle_mc_reference", "oracle_mc_uniform"):
             getattr(L, name).argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32, i64p]
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        for name in ("oracle_mc_reference_ranges", "oracle_mc_uniform_ranges"):
+            getattr(L, name).argtypes = [u8p, u64p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32,
+                                         u64p, u8p, i64p]
+        L.oracle_hand_class.argtypes = [ctypes.c_int, ctypes.c_int]
         L.oracle_enum_headsup.argtypes = [u8p, u8p, ctypes.c_int, i64p]
         L.oracle_enum_river_multi.argtypes = [u8p, u8p, ctypes.c_int, i64p]
         L.oracle_enum_reference_headsup.argtypes = [u8p, u8p, ctypes.c_int, i64p]
@@ -184,6 +189,58 @@ def mc_uniform(hero, board, players, runs, seed):
     if rc:
         raise ValueError("oracle_mc_uniform rc=%d" % rc)
     return out[0], out[1]
+
+
+def hand_class(c1, c2):
+    return lib().oracle_hand_class(int(c1), int(c2))
+
+
+def class_index(name):
+    """Class number (suited hi*13+lo, offsuit/pairs lo*13+hi) of a spelling like 'KAS', 'AKO', 'QQ'; None if the
+    reference's range test (montecarlo_python.py:24-34) could never produce that string."""
+    if len(name) == 2:
+        return RANKS.index(name[0]) * 14 if name[0] == name[1] and name[0] in RANKS else None
+    if len(name) == 3 and name[0] in RANKS and name[1] in RANKS and name[0] != name[1] and name[2] in "SO":
+        a, b = RANKS.index(name[0]), RANKS.index(name[1])
+        hi, lo = max(a, b), min(a, b)
+        return hi * 13 + lo if name[2] == "S" else lo * 13 + hi
+    return None
+
+
+def class_mask(names):
+    m = [0, 0, 0]
+    for n in names:
+        k = class_index(n)
+        if k is not None:
+            m[k >> 6] |= 1 << (k & 63)
+    return (ctypes.c_uint64 * 3)(*m)
+
+
+def _ranges_call(fn, hero, hero_classes, board, players, runs, seed, opp_classes, ghost):
+    b = ids(board)
+    h = ids(hero) if hero_classes is None else None
+    g = ids(ghost) if ghost else None
+    out = (ctypes.c_int64 * 12)()
+    rc = fn(_p(h) if h is not None else None, class_mask(hero_classes) if hero_classes is not None else None,
+            _p(b) if len(b) else None, len(b), int(players), int(runs), int(seed), class_mask(opp_classes),
+            _p(g) if g is not None else None, out)
+    if rc:
+        raise ValueError("oracle ranges call rc=%d" % rc)
+    return out
+
+
+def mc_reference_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None):
+    """run_montecarlo with an opponent range (set of class spellings), optionally a hero range and ghost cards, under
+    np.random.seed(seed): dict(wins, passes, win_types, next_randint).  `hero` is ignored when hero_classes is given."""
+    out = _ranges_call(lib().oracle_mc_reference_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost)
+    return {"wins": out[0], "passes": out[1], "win_types": {CAT_NAMES[i]: out[2 + i] for i in range(9) if out[2 + i]},
+            "next_randint": out[11]}
+
+
+def mc_uniform_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None):
+    """Unbiased dealing with ranges: (wins_strict, ties, attempts)."""
+    out = _ranges_call(lib().oracle_mc_uniform_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost)
+    return out[0], out[1], out[2]
 
 
 def enum_headsup(hero, board):

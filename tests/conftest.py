@@ -40,6 +40,18 @@ def golden_mc():
 
 
 @pytest.fixture(scope="session")
+def golden_ranges():
+    with open(os.path.join(GOLDEN, "mc_ranges_seeded.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_preflop():
+    with open(os.path.join(GOLDEN, "preflop_order.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
 def cuda_device():
     import torch
     if not torch.cuda.is_available():

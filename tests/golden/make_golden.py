@@ -17,6 +17,8 @@ Files written (all small, committed):
                        in UNIFORM dealing and, where enumerable, the exact expectation of the REFERENCE dealer
   mc_seeded.json       run_montecarlo under np.random.seed(s): wins / passes / win-type counts per spot, used to pin
                        the oracle's MT19937 + legacy randint + dealing restatement bit-exactly
+  preflop_order.json   the reference's ranking of the 169 starting-hand classes and the allowed sets of some fractions
+  mc_ranges_seeded.json seeded run_montecarlo runs with opponent ranges, hero ranges and ghost cards
 """
 import argparse
 import hashlib
@@ -358,6 +360,52 @@ def build_mc_seeded():
     print("mc_seeded.json written")
 
 
+def build_ranges():
+    """Ranges: the reference's ranking of the 169 starting-hand classes (get_opponent_allowed_cards_list), the allowed
+    sets of a few fractions, and seeded run_montecarlo runs with an opponent range, a hero RANGE (player_card_list[0]
+    is a set) and ghost cards (reference tests test_montecarlo20/21 use range 0.25 and the hero set {'AKO','AA'})."""
+    import operator
+    mc = montecarlo_python.MonteCarlo()
+    mc.get_opponent_allowed_cards_list(1)
+    order = [k for k, _ in sorted(mc.preflop_equities.items(), key=operator.itemgetter(1))]
+    fractions = {str(x): sorted(mc.get_opponent_allowed_cards_list(x)) for x in (0.25, 0.5, 0.1, 0.01, 0.004, 1, 1.5, 0.999)}
+    with open(os.path.join(HERE, "preflop_order.json"), "w") as f:
+        json.dump({"source": "tools/montecarlo_python.py:37-110, keys of preflop_equities sorted ascending by value",
+                   "order": order, "allowed": fractions}, f, indent=1)
+    out = {"source": "MonteCarlo.run_montecarlo under np.random.seed(seed), timeout=+1e9 s, with opponent_range / hero "
+                     "range / ghost cards", "numpy": np.__version__, "runs": []}
+    cases = [
+        # name, hero (list of cards or set of classes), board, players, runs, opponent_range, ghost
+        ("t20", ['KS', 'KC'], ['3D', '9H', 'AS', '7S', 'QH'], 3, 1500, 0.25, ''),
+        ("t21", {'AKO', 'AA'}, ['3D', '9H', 'AS', '7S', 'QH'], 3, 800, 0.25, ''),
+        ("pre2_r10", ['QS', 'QH'], [], 2, 1500, 0.1, ''),
+        ("flop4_r50", ['AS', 'KS'], ['2C', '7D', 'KH'], 4, 1000, 0.5, ''),
+        ("turn3_set", ['9D', '9C'], ['2C', '7D', 'KH', 'TS'], 3, 1000, {'AKS', 'KAO', 'QQ', 'JJ', '9TS', 'T9O'}, ''),
+        ("flop3_ghost", ['AS', 'KS'], ['2C', '7D', 'KH'], 3, 1000, 1, ['AH', 'AD']),
+        ("hero_set_pre", {'AKS', 'QQ', '78S'}, [], 2, 600, 0.5, ''),
+        ("tiny_range", ['5H', '5D'], ['5C', 'KD', '2S'], 2, 800, 0.004, ''),
+    ]
+    for name, hero, board, players, runs, rng, ghost in cases:
+        for seed in (3, 777):
+            np.random.seed(seed)
+            m = montecarlo_python.MonteCarlo()
+            first = set(hero) if isinstance(hero, set) else list(hero)
+            m.run_montecarlo([first], list(board), players, 1, maxRuns=runs, timeout=time.time() + 1e9,
+                             ghost_cards=ghost, opponent_range=rng)
+            wins = int(round(m.equity * m.runs))
+            types = {k: int(round(v * m.runs)) for k, v in m.winnerCardTypeList.items()}
+            assert sum(types.values()) == wins
+            out["runs"].append({"name": name, "hero": sorted(hero) if isinstance(hero, set) else hero,
+                                "hero_is_range": isinstance(hero, set), "board": board, "players": players,
+                                "seed": seed, "runs": m.runs, "opponent_range": sorted(rng) if isinstance(rng, set) else rng,
+                                "ghost": list(ghost) if ghost else [], "wins": wins, "passes": int(m.passes),
+                                "win_types": types, "next_randint_0_1000000": int(np.random.randint(0, 1000000))})
+        print(" ranges", name, out["runs"][-1]["wins"], "/", runs, "passes", out["runs"][-1]["passes"])
+    with open(os.path.join(HERE, "mc_ranges_seeded.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("mc_ranges_seeded.json written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -371,6 +419,8 @@ def main():
         build_mc_seeded()
     if not only or "enum" in only:
         build_enum(a.quick)
+    if not only or "ranges" in only:
+        build_ranges()
 
 
 if __name__ == "__main__":

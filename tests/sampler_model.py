@@ -86,11 +86,94 @@ def deal_reference(seed, query, trial, hole, board, players):
     return opp, full, passes
 
 
-def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_offset=0):
-    """dict(wins, ties, passes, win_types[9]) of the modelled sampler scored by the oracle's rank ids."""
+RANGES_BLOCK0 = {"reference": 0x80000000, "uniform": 0xC0000000}
+MAX_ATTEMPTS = 1 << 16
+
+
+def hand_class(c1, c2):
+    """Starting-hand class number: suited hi*13+lo, offsuit and pairs lo*13+hi (rank indices, hi >= lo)."""
+    r1, r2 = c1 >> 2, c2 >> 2
+    hi, lo = max(r1, r2), min(r1, r2)
+    return hi * 13 + lo if (c1 & 3) == (c2 & 3) else lo * 13 + hi
+
+
+def _allowed(mask, c1, c2):
+    k = hand_class(c1, c2)
+    return (int(mask[k >> 6]) >> (k & 63)) & 1
+
+
+def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None):
+    """equity_ranges_kernel: dealing with an opponent range (169-bit mask, three 64-bit words), optionally a hero drawn
+    from a range (`hole` ignored) and ghost cards removed from the deck.  Returns (hero, opponents, full board, passes).
+
+    One Philox word per attempt: i1 = hi32(w*n), i2 = hi32(lo32(w*n)*(n-1)) on the ordered list of unseen cards.
+      reference: the Python reference, montecarlo_python.py:136-181 -- retry while i1 == i2 or the class of
+                 (deck[i1], deck[i2]) is not allowed (both read BEFORE popping); a hero keeps exactly those two cards;
+                 an opponent gets deck.pop(i1) then deck.pop(i2) from the shortened list; board card j = hi32(w*(n-1)).
+      uniform:   c1 = deck[i1], c2 = (deck without c1)[i2], retry while their class is not allowed; board j = hi32(w*n).
+    """
+    known = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set())
+    deck = [c for c in range(52) if c not in known]
+    ws = _Words(seed, query, trial)
+    ws.blk = RANGES_BLOCK0[mode]
+    passes = 0
+
+    def draw(mask, is_hero):
+        nonlocal passes
+        n = len(deck)
+        for _ in range(MAX_ATTEMPTS):
+            passes += 1
+            prod = ws.next() * n
+            i1, i2 = prod >> 32, ((prod & MASK) * (n - 1)) >> 32
+            if mode == "reference":
+                if i1 == i2 or not _allowed(mask, deck[i1], deck[i2]):
+                    continue
+                if is_hero:
+                    c1, c2 = deck[i1], deck[i2]
+                    deck.remove(c1)
+                    deck.remove(c2)
+                else:
+                    c1 = deck.pop(i1)
+                    c2 = deck.pop(i2)
+                return [c1, c2]
+            c1 = deck[i1]
+            c2 = (deck[:i1] + deck[i1 + 1:])[i2]
+            if not _allowed(mask, c1, c2):
+                continue
+            deck.remove(c1)
+            deck.remove(c2)
+            return [c1, c2]
+        raise RuntimeError("range cannot be satisfied")
+
+    hero = list(hole) if hero_mask is None else draw(hero_mask, True)
+    opp = [draw(opp_mask, False) for _ in range(players - 1)]
+    full = list(board)
+    while len(full) < 5:
+        n = len(deck)
+        j = (ws.next() * (n - 1 if mode == "reference" else n)) >> 32
+        full.append(deck.pop(j))
+    return hero, opp, full, passes
+
+
+def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_offset=0, opp_mask=None, hero_mask=None,
+              ghost=None):
+    """dict(wins, ties, passes, win_types[9]) of the modelled sampler scored by the oracle's rank ids.  With `opp_mask`
+    the range dealers (deal_ranges) are modelled, otherwise the plain ones."""
     wins = ties = passes = 0
     types = [0] * 9
     for t in range(trial_offset, trial_offset + trials):
+        if opp_mask is not None:
+            hole_t, opp, full, p = deal_ranges(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
+            passes += p
+            hv = oracle.rank7(list(hole_t) + full)
+            best = max([oracle.rank7(o + full) for o in opp], default=-1)
+            if hv > best:
+                wins += 1
+            elif hv == best:
+                ties += 1
+            if hv >= best:
+                types[oracle.type7(list(hole_t) + full)] += 1
+            continue
         if mode == "uniform":
             opp, full = deal_uniform(seed, query, t, hole, board, players)
         else:

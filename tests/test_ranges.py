@@ -1,0 +1,197 @@
+"""Opponent ranges, hero ranges and ghost cards (reference tools/montecarlo_python.py:24-112, :136-181,
+:206-208; reference tests test_montecarlo20/21, tests/test_montecarlo_python.py:215-232).
+
+CPU part: the oracle's range-aware restatement against seeded runs of the unmodified reference, and the host-side range
+tables against the reference's own ranking.  GPU part (-m gpu): libnpk's range kernels against the sampler specification
+(bit-exact) and against the oracle (3 sigma)."""
+import numpy as np
+import pytest
+
+import oracle
+import sampler_model
+from neuron_poker_b200 import ranges
+
+
+def _opp_classes(run):
+    r = run["opponent_range"]
+    return set(r) if isinstance(r, list) else ranges.allowed_classes(r)
+
+
+def test_preflop_order_is_the_references(golden_preflop):
+    assert ranges.PREFLOP_ORDER == golden_preflop["order"]
+    assert len({ranges.class_index(n) for n in ranges.PREFLOP_ORDER}) == 169
+    for x, names in golden_preflop["allowed"].items():
+        assert sorted(ranges.allowed_classes(float(x))) == names, x
+    assert len(ranges.allowed_classes(0.004)) == 169          # take_top == 0 -> [-0:] is the whole list
+
+
+def test_class_numbering_agrees_everywhere():
+    for c1 in range(52):
+        for c2 in range(52):
+            if c1 != c2:
+                k = oracle.hand_class(c1, c2)
+                assert k == ranges.class_of_cards(c1, c2) == sampler_model.hand_class(c1, c2)
+                name = oracle.RANKS[c1 >> 2] + oracle.RANKS[c2 >> 2] + ("" if c1 >> 2 == c2 >> 2 else
+                                                                        "S" if (c1 & 3) == (c2 & 3) else "O")
+                assert ranges.class_index(name) == k == oracle.class_index(name)
+    assert ranges.class_index("AAO") is None and ranges.class_index("AK") is None and ranges.class_index("1KS") is None
+
+
+def test_oracle_reproduces_reference_range_runs(golden_ranges):
+    """wins, passes, win types and the RNG stream position, bit for bit, under np.random.seed(s)."""
+    assert len(golden_ranges["runs"]) == 16
+    for run in golden_ranges["runs"]:
+        hero_classes = set(run["hero"]) if run["hero_is_range"] else None
+        got = oracle.mc_reference_ranges(None if run["hero_is_range"] else run["hero"], run["board"], run["players"],
+                                         run["runs"], run["seed"], _opp_classes(run), hero_classes=hero_classes,
+                                         ghost=run["ghost"] or None)
+        assert got["wins"] == run["wins"], run["name"]
+        assert got["passes"] == run["passes"], run["name"]
+        assert got["win_types"] == run["win_types"], run["name"]
+        assert got["next_randint"] == run["next_randint_0_1000000"], run["name"]
+
+
+def test_sampler_specification_with_ranges_converges_to_the_oracle():
+    """The Philox-driven specification of libnpk's range dealers (tests/sampler_model.py) and the oracle's MT19937-driven
+    restatement sample the same distributions: equities agree within 3 sigma of their combined standard error."""
+    cases = [("reference", ["KS", "KC"], None, ["3D", "9H", "AS", "7S", "QH"], 3, ranges.allowed_classes(0.25), None),
+             ("reference", None, {"AKO", "AA"}, ["3D", "9H", "AS", "7S", "QH"], 3, ranges.allowed_classes(0.25), None),
+             ("uniform", ["AS", "KS"], None, ["2C", "7D", "KH"], 3, ranges.allowed_classes(0.5), ["AH", "AD"]),
+             ("uniform", None, {"QQ", "AKS", "78S"}, [], 2, ranges.allowed_classes(0.3), None)]
+    T = 6000
+    for mode, hero, hero_cls, board, players, opp, ghost in cases:
+        h = [oracle.card_id(c) for c in hero] if hero else None
+        b = [oracle.card_id(c) for c in board]
+        g = [oracle.card_id(c) for c in ghost] if ghost else None
+        m = sampler_model.run_model(oracle, mode, 99, 0, h, b, players, T, opp_mask=ranges.mask_from_classes(opp),
+                                    hero_mask=ranges.mask_from_classes(hero_cls) if hero_cls else None, ghost=g)
+        p_model = (m["wins"] + m["ties"]) / T
+        if mode == "reference":
+            o = oracle.mc_reference_ranges(hero, board, players, 40000, 5, opp, hero_classes=hero_cls, ghost=ghost)
+            p_or = o["wins"] / 40000
+            passes_or = o["passes"] / 40000
+            assert abs(m["passes"] / T - passes_or) < 0.05 * passes_or + 0.05
+        else:
+            w, t, _ = oracle.mc_uniform_ranges(hero, board, players, 40000, 5, opp, hero_classes=hero_cls, ghost=ghost)
+            p_or = (w + t) / 40000
+        se = (p_or * (1 - p_or) * (1 / T + 1 / 40000)) ** 0.5
+        assert abs(p_model - p_or) < 3 * se + 1e-9, (mode, hero, hero_cls, p_model, p_or, se)
+
+
+# ---- GPU: libnpk's range kernels ---------------------------------------------------------------------------------------
+def _ids(cards):
+    return [oracle.card_id(c) for c in cards]
+
+
+RANGE_CASES = [
+    # mode, hero cards, hero classes, board, players, opponent range, ghost
+    ("reference", ["KS", "KC"], None, ["3D", "9H", "AS", "7S", "QH"], 3, 0.25, None),
+    ("reference", None, {"AKO", "AA"}, ["3D", "9H", "AS", "7S", "QH"], 3, 0.25, None),
+    ("reference", ["AS", "KS"], None, ["2C", "7D", "KH"], 4, 0.5, ["AH", "AD"]),
+    ("reference", ["QS", "QH"], None, [], 2, 0.1, None),
+    ("reference", ["9D", "9C"], None, ["2C", "7D", "KH", "TS"], 6, {"AKS", "KAO", "QQ", "JJ", "9TS", "T9O", "23O"}, None),
+    ("uniform", ["KS", "KC"], None, ["3D", "9H", "AS", "7S", "QH"], 3, 0.25, None),
+    ("uniform", None, {"QQ", "AKS", "78S"}, [], 2, 0.3, None),
+    ("uniform", ["AS", "KS"], None, ["2C", "7D", "KH"], 5, 0.5, ["AH", "AD"]),
+    ("uniform", ["5H", "5D"], None, ["5C", "KD", "2S", "2D"], 10, 1, None),
+]
+
+
+@pytest.mark.gpu
+def test_range_kernels_match_the_sampler_specification(cuda_device):
+    """wins, ties, passes and win types of equity_ranges_kernel equal the Python specification scored by the oracle,
+    bit for bit, in both dealing modes, with hero ranges and ghost cards, at a trial offset."""
+    import neuron_poker_b200 as npk
+    T, off = 96, 1000
+    for i, (mode, hero, hero_cls, board, players, opp, ghost) in enumerate(RANGE_CASES):
+        b = _ids(board)
+        out = npk.get_equity_ranges_batch(
+            None if hero is None else np.array([_ids(hero)], dtype=np.uint8),
+            np.array([b + [255] * (5 - len(b))], dtype=np.uint8), np.array([players], dtype=np.uint8), T,
+            opponent_range=opp, hero_range=hero_cls, ghost=None if ghost is None else np.array([_ids(ghost)], dtype=np.uint8),
+            seed_value=77 + i, deal_mode=mode, trial_offset=off, query_offset=5, win_types=True, passes=True)
+        m = sampler_model.run_model(oracle, mode, 77 + i, 5, _ids(hero) if hero else None, b, players, T, trial_offset=off,
+                                    opp_mask=ranges.opponent_mask(opp),
+                                    hero_mask=ranges.mask_from_classes(hero_cls) if hero_cls else None,
+                                    ghost=_ids(ghost) if ghost else None)
+        got = (int(out["wins"][0]), int(out["ties"][0]), int(out["passes"][0]), [int(x) for x in out["win_types"][0]])
+        assert got == (m["wins"], m["ties"], m["passes"], m["win_types"]), (mode, hero, hero_cls, got, m)
+
+
+@pytest.mark.gpu
+def test_full_range_reference_mode_equals_the_plain_reference_kernel(cuda_device):
+    """With every class allowed, a fixed hero and no ghost cards the range kernel consumes the same Philox words in the
+    same way as equity_reference_kernel: identical counters."""
+    import neuron_poker_b200 as npk
+    rng = np.random.default_rng(3)
+    Q = 24
+    cards = np.stack([rng.permutation(52)[:7] for _ in range(Q)]).astype(np.uint8)
+    hole, board = cards[:, :2].copy(), cards[:, 2:7].copy()
+    npl = rng.integers(2, 11, Q).astype(np.uint8)
+    for q in range(Q):
+        board[q, [0, 3, 4, 5][q % 4]:] = 255
+    a = npk.get_equity_batch(hole, board, npl, 3000, seed_value=9, deal_mode="reference", passes=True, win_types=True)
+    b = npk.get_equity_ranges_batch(hole, board, npl, 3000, opponent_range=1, seed_value=9, deal_mode="reference",
+                                    passes=True, win_types=True)
+    for k in ("wins", "ties", "passes", "win_types"):
+        assert (a[k] == b[k]).all(), k
+
+
+@pytest.mark.gpu
+def test_range_kernels_within_3_sigma_of_the_oracle(cuda_device):
+    """4 M GPU trials against 400 k oracle trials (MT19937-driven restatement of the reference dealer with ranges, resp.
+    its unbiased counterpart): |p_gpu - p_oracle| < 3 * combined standard error; mean attempts per trial agree."""
+    import neuron_poker_b200 as npk
+    T, TO = 4_000_000, 400_000
+    for i, (mode, hero, hero_cls, board, players, opp, ghost) in enumerate(RANGE_CASES[:8]):
+        b = _ids(board)
+        out = npk.get_equity_ranges_batch(
+            None if hero is None else np.array([_ids(hero)], dtype=np.uint8),
+            np.array([b + [255] * (5 - len(b))], dtype=np.uint8), np.array([players], dtype=np.uint8), T,
+            opponent_range=opp, hero_range=hero_cls, ghost=None if ghost is None else np.array([_ids(ghost)], dtype=np.uint8),
+            seed_value=1234 + i, deal_mode=mode, passes=True)
+        p_gpu = (int(out["wins"][0]) + int(out["ties"][0])) / T
+        opp_cls = opp if isinstance(opp, set) else ranges.allowed_classes(opp)
+        if mode == "reference":
+            o = oracle.mc_reference_ranges(hero, board, players, TO, 11 + i, opp_cls, hero_classes=hero_cls, ghost=ghost)
+            p_or, att = o["wins"] / TO, o["passes"] / TO
+        else:
+            w, t, a = oracle.mc_uniform_ranges(hero, board, players, TO, 11 + i, opp_cls, hero_classes=hero_cls, ghost=ghost)
+            p_or, att = (w + t) / TO, a / TO
+        se = (p_or * (1 - p_or) * (1 / T + 1 / TO)) ** 0.5
+        assert abs(p_gpu - p_or) < 3 * se + 1e-9, (mode, hero, hero_cls, p_gpu, p_or, se)
+        assert abs(int(out["passes"][0]) / T - att) < 0.02 * att, (mode, int(out["passes"][0]) / T, att)
+
+
+@pytest.mark.gpu
+def test_reference_range_tests_20_and_21(cuda_device):
+    """reference tests/test_montecarlo_python.py:215-232 through the MonteCarlo mirror, with the reference's own
+    acceptance rule (|mean of 5 runs - expected| < 3 points, stdev < 3, win types sum to the equity)."""
+    import neuron_poker_b200 as npk
+    npk.seed(2024)
+    sim = npk.MonteCarlo()
+    for my_cards, expected in (([['KS', 'KC']], 12.8), ([{'AKO', 'AA'}], 77.8)):
+        res = []
+        for _ in range(5):
+            sim.run_montecarlo(my_cards, ['3D', '9H', 'AS', '7S', 'QH'], 3, 1, maxRuns=15000, timeout=0, ghost_cards='',
+                               opponent_range=0.25)
+            res.append(sim.equity * 100)
+            assert abs(sum(sim.winnerCardTypeList.values()) - sim.equity) < 1e-4
+            assert sim.runs == 15000 and sim.passes >= 2 * 15000
+        assert abs(np.mean(res) - expected) < 3 and np.std(res) < 3, (my_cards, res)
+    npk.seed(None)
+
+
+@pytest.mark.gpu
+def test_unsatisfiable_range_is_an_error_not_a_hang(cuda_device):
+    import neuron_poker_b200 as npk
+    from neuron_poker_b200._lib import NpkError
+    with pytest.raises(NpkError) as ei:        # no ace is left for an opponent who must hold AA
+        npk.equity_counts_ranges(['AS', 'AH'], ['AD', 'AC', '2S'], 2, 5000, opponent_range={'AA'})
+    assert ei.value.code == -6
+    with pytest.raises(NpkError) as ei:        # spellings the reference's test can never produce
+        npk.equity_counts_ranges(['AS', 'AH'], [], 2, 100, opponent_range={'AAO', 'AK'})
+    assert ei.value.code == -6
+    with pytest.raises(NpkError) as ei:        # ghost card that is also on the board: list.index fails in the reference
+        npk.equity_counts_ranges(['AS', 'AH'], ['2C', '7D', 'KH'], 2, 100, opponent_range=1, ghost_cards=['KH', '3S'])
+    assert ei.value.code == -5
