@@ -302,6 +302,28 @@ def main():
     e2e_s = float(t.item())
     e2e_value = Q * t_cnt * P * world * e2e_steps / e2e_s
 
+    # the other half of BASELINE.json's metric: blocking get_equity calls per second at 10,000 trials, 6 players
+    # (string parsing, H2D, launch, sync and D2H all inside; reference dealer, like the reference's own get_equity)
+    calls = None
+    if rank == 0:
+        for _ in range(20):
+            npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
+        n_calls = 300
+        c0 = time.perf_counter()
+        for _ in range(n_calls):
+            npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
+        calls = n_calls / (time.perf_counter() - c0)
+
+    kernel_name = "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_reference_kernel"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t_rec = json.load(f).get(kernel_name)
+        if t_rec and wl["name"].startswith("cfg3"):
+            traffic = t_rec["dram_bytes_read"] + t_rec["dram_bytes_write"]
+    except Exception:
+        pass
+
     a_instr = algorithmic_instr(P, B)
     kernel_ms = dev_ms / args.steps
     achieved = Q * t_cnt * a_instr / (kernel_ms * 1e-3)          # per GPU
@@ -318,9 +340,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * Q), "d2h_bytes_per_step": int(16 * Q),
                 "steps": e2e_steps, "api": "neuron_poker_b200.equity_counts_batch -> npk_equity_host"},
         "gpu_launches": args.steps,
+        "get_equity_calls_per_s": calls,
         "roofline": {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tthread-instr/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
-                     "kernel": "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_reference_kernel",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json); "
+                                     "the kernel is bound by integer issue and shared memory, not HBM",
+                     "kernel": kernel_name,
                      "algorithmic_instr_per_trial": a_instr, "peak_source": "npk_int_peak measured in this run",
                      "peak_variants": peak_detail, "nominal_issue_peak": 148 * 128 * 1.965e9 / 1e12},
     }
@@ -329,6 +354,8 @@ def main():
         cores = host_cores()
         if oracle.ref_available():
             n = min(max(1, Q), 2 * cores)
+            v, dt = reference_sample(wl, hole_h, board_h, npl_h, n, cores)
+            n = int(max(n, min(Q if Q > 1 else 64, n * 12.0 / max(dt, 1e-3))))      # about 12 s of host work
             v, dt = reference_sample(wl, hole_h, board_h, npl_h, n, cores)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                                     "sample": "%d queries x %d trials through the reference C++ montecarlo() "
