@@ -9,6 +9,8 @@
 #include <vector>
 
 #include "../../include/npk.h"
+#include "../../include/npk_holdem.h"
+#include "npk_holdem_launch.h"
 #include "npk_kernels.h"
 #include "npk_tables.h"
 
@@ -643,6 +645,89 @@ int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uin
     cudaError_t e = npk::launch_showdown(ds->t, holes, n_players, board, N, maxp, winner, wtype, ranks,
                                          grid_for(*ds, (N + 31) / 32, npk::kAuxThreads / 32), static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "showdown_kernel launch");
+}
+
+// ---- vectorised HoldemTable (include/npk_holdem.h) ------------------------------------------------------------------------
+int64_t npk_holdem_table_bytes(void) { return (int64_t)sizeof(NpkHoldemTable); }
+
+int npk_holdem_init(void* tables, int64_t N, int n_players, double initial_stacks, double small_blind, double big_blind,
+                    int max_raises_per_player_round, const uint8_t* autoplay, uint64_t seed, int64_t table_offset,
+                    void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (n_players < 2 || n_players > NPK_MAX_SEATS) return fail(NPK_ERR_INVALID_ARGUMENT, "2..10 players per table");
+    if (max_raises_per_player_round < 1 || max_raises_per_player_round > 100)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "max_raises_per_player_round must be 1..100");
+    if (!(initial_stacks > 0) || !(small_blind > 0) || !(big_blind > 0))
+        return fail(NPK_ERR_INVALID_ARGUMENT, "stacks and blinds must be positive");
+    npk::HoldemInit cfg{};
+    cfg.n_players = n_players; cfg.max_raises = max_raises_per_player_round;
+    cfg.initial_stacks = initial_stacks; cfg.small_blind = small_blind; cfg.big_blind = big_blind;
+    for (int i = 0; i < n_players; i++) cfg.autoplay[i] = autoplay ? autoplay[i] : 0;
+    cudaError_t e = npk::launch_holdem_init(ds->t, tables, N, cfg, seed, table_offset, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_init_kernel launch");
+}
+
+int npk_holdem_reset_done(void* tables, int64_t N, uint64_t seed, int64_t table_offset, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    cudaError_t e = npk::launch_holdem_reset_done(ds->t, tables, N, seed, table_offset, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_reset_done_kernel launch");
+}
+
+int npk_holdem_step(void* tables, int64_t N, const int8_t* actions, double* rewards, uint64_t seed, int64_t table_offset,
+                    void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables || !actions) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaError_t e = npk::launch_holdem_step(ds->t, tables, N, actions, rewards, seed, table_offset, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_step_kernel launch");
+}
+
+int npk_holdem_queries(const void* tables, int64_t N, uint8_t* hole, uint8_t* board, uint8_t* n_players, uint8_t* active,
+                       void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables || !hole || !board || !n_players) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaError_t e = npk::launch_holdem_queries(tables, N, hole, board, n_players, active, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_queries_kernel launch");
+}
+
+int npk_holdem_decide(const void* tables, int64_t N, const uint64_t* wins, const uint64_t* ties, int64_t runs,
+                      const double* equity, const uint8_t* agent_kind, const double* min_call_equity,
+                      const double* min_bet_equity, uint64_t seed, int64_t decision_counter, int64_t table_offset,
+                      int8_t* actions, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables || !actions || !agent_kind) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (!equity && (!wins || !ties || runs <= 0))
+        return fail(NPK_ERR_INVALID_ARGUMENT, "pass either equity or wins + ties + runs");
+    npk::HoldemAgents ag{};
+    for (int i = 0; i < NPK_MAX_SEATS; i++) {
+        ag.kind[i] = agent_kind[i];
+        ag.min_call_equity[i] = min_call_equity ? min_call_equity[i] : 0.0;
+        ag.min_bet_equity[i] = min_bet_equity ? min_bet_equity[i] : 0.0;
+    }
+    cudaError_t e = npk::launch_holdem_decide(ds->t, tables, N, wins, ties, runs, equity, ag, seed,
+                                              (unsigned long long)decision_counter, table_offset, actions,
+                                              static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_decide_kernel launch");
 }
 
 int npk_int_peak(int variant, int iters, double* thread_instr_per_s, float* ms_out)

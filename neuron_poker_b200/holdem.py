@@ -1,0 +1,227 @@
+"""Vectorised HoldemTable: N independent tables advanced in lock step on the GPU (include/npk_holdem.h).
+
+Mirror of the reference's gym_env/env.py::HoldemTable for the part a self-play loop needs -- the betting state machine
+(gym_env/cycle.py), card dealing (env.py:667-688), showdown (env.py:573-605), legal moves (:629-658), rewards (:280-306)
+-- with the same attribute names, as tensors with a leading table dimension:
+
+    tables = HoldemTables(65536, n_players=6, initial_stacks=100, small_blind=1, big_blind=2)
+    tables.step(actions)                    # env.step(action) for every table (int8 CUDA tensor / array of Action values)
+    tables.selfplay_step(agents)            # get_equity for every current player + agent decision + step, all on the GPU
+    s = tables.state()                      # host copy: numpy structured array, one record per table
+
+`Action` and `Stage` carry the reference's values (gym_env/enums.py).
+"""
+import ctypes
+from enum import IntEnum
+
+import numpy as np
+
+from . import _lib
+
+MAX_SEATS = 10
+
+
+class Action(IntEnum):
+    FOLD = 0
+    CHECK = 1
+    CALL = 2
+    RAISE_3BB = 3
+    RAISE_HALF_POT = 4
+    RAISE_POT = 5
+    RAISE_2POT = 6
+    ALL_IN = 7
+    SMALL_BLIND = 8
+    BIG_BLIND = 9
+
+
+class Stage(IntEnum):
+    PREFLOP = 0
+    FLOP = 1
+    TURN = 2
+    RIVER = 3
+    END_HIDDEN = 4
+    SHOWDOWN = 5
+
+
+AGENT_EQUITY, AGENT_RANDOM = 0, 1
+
+_S = MAX_SEATS
+TABLE_DTYPE = np.dtype([
+    ("stack", "f8", (_S,)), ("player_pots", "f8", (_S,)), ("player_max_win", "f8", (_S,)), ("funds_prev", "f8", (_S,)),
+    ("funds_last", "f8", (_S,)), ("community_pot", "f8"), ("current_round_pot", "f8"), ("min_call", "f8"),
+    ("last_player_pot", "f8"), ("reward", "f8"), ("small_blind", "f8"), ("big_blind", "f8"), ("initial_stacks", "f8"),
+    ("rng_counter", "u8"),
+    ("idx", "i4"), ("dealer_idx", "i4"), ("step_counter", "i4"), ("cycle_round_number", "i4"), ("max_steps_total", "i4"),
+    ("last_raiser_step", "i4"), ("max_steps_after_raiser", "i4"), ("max_steps_after_big_blind", "i4"), ("last_raiser", "i4"),
+    ("checkers", "i4"), ("max_remaining_steps_without_raising", "i4"),
+    ("stage", "i4"), ("current_player", "i4"), ("winner_ix", "i4"), ("dealer_pos", "i4"), ("done", "i4"), ("funds_rows", "i4"),
+    ("n_players", "i4"), ("max_raises", "i4"), ("n_table_cards", "i4"), ("n_deck", "i4"), ("acting_agent", "i4"),
+    ("hands_played", "i4"), ("error", "i4"), ("legal_moves", "u4"),
+    ("can_still", "u1", (_S,)), ("out_of_cash", "u1", (_S,)), ("folder", "u1", (_S,)), ("alive", "u1", (_S,)),
+    ("first_action", "u1", (_S,)), ("autoplay", "u1", (_S,)), ("num_raises", "u1", (_S, 4)), ("cards", "u1", (_S, 2)),
+    ("table_cards", "u1", (5,)), ("deck", "u1", (52,)), ("reserved", "u1", (5,)),
+], align=True)
+
+
+def _bind(L):
+    if getattr(L, "_holdem_bound", False):
+        return L
+    vp, i64, i32, f64, u64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double, ctypes.c_uint64
+    L.npk_holdem_table_bytes.restype = i64
+    L.npk_holdem_init.argtypes = [vp, i64, i32, f64, f64, f64, i32, vp, u64, i64, vp]
+    L.npk_holdem_reset_done.argtypes = [vp, i64, u64, i64, vp]
+    L.npk_holdem_step.argtypes = [vp, i64, vp, vp, u64, i64, vp]
+    L.npk_holdem_queries.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    L.npk_holdem_decide.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, u64, i64, i64, vp, vp]
+    if L.npk_holdem_table_bytes() != TABLE_DTYPE.itemsize:
+        raise RuntimeError("NpkHoldemTable is %d bytes in libnpk.so but %d in holdem.TABLE_DTYPE"
+                           % (L.npk_holdem_table_bytes(), TABLE_DTYPE.itemsize))
+    L._holdem_bound = True
+    return L
+
+
+class EquityAgents(object):
+    """Per-seat agents of a self-play table: agent_consider_equity players (min_call_equity, min_bet_equity;
+    agents/agent_consider_equity.py:12-19) and random players (agents/agent_random.py)."""
+
+    def __init__(self, n_players):
+        self.kind = np.zeros(MAX_SEATS, dtype=np.uint8)
+        self.min_call_equity = np.zeros(MAX_SEATS, dtype=np.float64)
+        self.min_bet_equity = np.zeros(MAX_SEATS, dtype=np.float64)
+        self.n_players = n_players
+
+    def equity(self, seat, min_call_equity, min_bet_equity):
+        self.kind[seat] = AGENT_EQUITY
+        self.min_call_equity[seat] = min_call_equity
+        self.min_bet_equity[seat] = min_bet_equity
+        return self
+
+    def random(self, seat):
+        self.kind[seat] = AGENT_RANDOM
+        return self
+
+    @staticmethod
+    def equity_vs_random():
+        """main.py:136-150: four equity players and two random ones."""
+        a = EquityAgents(6)
+        a.equity(0, .5, -.5).equity(1, .8, -.8).equity(2, .7, -.7).equity(3, .2, -.3).random(4).random(5)
+        return a
+
+
+class HoldemTables(object):
+    """N tables of the reference's HoldemTable (same constructor arguments, env.py:67-69), created, dealt and reset on
+    the current CUDA device.  `autoplay` marks seats that are autoplay agents (it only decides the sign of the final
+    reward, env.py:294-296)."""
+
+    def __init__(self, n_tables, n_players=6, initial_stacks=100, small_blind=1, big_blind=2,
+                 max_raises_per_player_round=2, autoplay=None, seed=0, table_offset=0, device=None):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.L = _bind(_lib.ensure_init(self.device.index if self.device.index is not None else 0))
+        self.n_tables, self.n_players = int(n_tables), int(n_players)
+        self.seed, self.table_offset = int(seed), int(table_offset)
+        self.params = (float(initial_stacks), float(small_blind), float(big_blind), int(max_raises_per_player_round))
+        self.autoplay = np.zeros(MAX_SEATS, dtype=np.uint8)
+        if autoplay is not None:
+            self.autoplay[:len(autoplay)] = np.asarray(autoplay, dtype=np.uint8)
+        nbytes = TABLE_DTYPE.itemsize * self.n_tables
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        self.rewards = torch.zeros(self.n_tables, dtype=torch.float64, device=self.device)
+        self.decisions = 0
+        self._q = None
+        self.reset()
+
+    # ---- plumbing ----
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _u64(self, v):
+        return ctypes.c_uint64(int(v) & (2**64 - 1))
+
+    def reset(self):
+        """HoldemTable.reset() for every table (env.py:138-168): fresh stacks, first hand dealt, blinds posted."""
+        st, sb, bb, mr = self.params
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_init(self.buf.data_ptr(), self.n_tables, self.n_players, st, sb, bb, mr,
+                                              self.autoplay.ctypes.data_as(ctypes.c_void_p), self._u64(self.seed),
+                                              self.table_offset, self._stream()))
+        return self
+
+    def reset_done(self):
+        """Start a new game on every finished table."""
+        with self.torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_reset_done(self.buf.data_ptr(), self.n_tables, self._u64(self.seed),
+                                                    self.table_offset, self._stream()))
+
+    def step(self, actions):
+        """env.step(action) on every table.  `actions`: int8 CUDA tensor, or anything array-like of Action values;
+        negative = leave that table alone.  Returns the rewards tensor [N] (float64, CUDA)."""
+        torch = self.torch
+        if not isinstance(actions, torch.Tensor):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.int8))
+        actions = actions.to(self.device, dtype=torch.int8).contiguous()
+        assert actions.numel() == self.n_tables
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_step(self.buf.data_ptr(), self.n_tables, actions.data_ptr(), self.rewards.data_ptr(),
+                                              self._u64(self.seed), self.table_offset, self._stream()))
+        return self.rewards
+
+    def queries(self):
+        """The get_equity arguments of _get_environment (env.py:249-264) for every table, as CUDA uint8 tensors
+        (hole [N,2], board [N,5], n_players [N], active [N])."""
+        torch = self.torch
+        if self._q is None:
+            n = self.n_tables
+            self._q = (torch.empty((n, 2), dtype=torch.uint8, device=self.device),
+                       torch.empty((n, 5), dtype=torch.uint8, device=self.device),
+                       torch.empty(n, dtype=torch.uint8, device=self.device),
+                       torch.empty(n, dtype=torch.uint8, device=self.device))
+        hole, board, npl, active = self._q
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_queries(self.buf.data_ptr(), self.n_tables, hole.data_ptr(), board.data_ptr(),
+                                                 npl.data_ptr(), active.data_ptr(), self._stream()))
+        return hole, board, npl, active
+
+    def decide(self, agents, equity=None, wins=None, ties=None, runs=0):
+        """Agent decisions for every table from an equity tensor [N] (float64) or from Monte-Carlo counters."""
+        torch = self.torch
+        actions = torch.empty(self.n_tables, dtype=torch.int8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_decide(
+                self.buf.data_ptr(), self.n_tables, wins.data_ptr() if wins is not None else None,
+                ties.data_ptr() if ties is not None else None, int(runs), equity.data_ptr() if equity is not None else None,
+                agents.kind.ctypes.data_as(ctypes.c_void_p), agents.min_call_equity.ctypes.data_as(ctypes.c_void_p),
+                agents.min_bet_equity.ctypes.data_as(ctypes.c_void_p), self._u64(self.seed), self.decisions,
+                self.table_offset, actions.data_ptr(), self._stream()))
+        self.decisions += 1
+        return actions
+
+    def selfplay_step(self, agents, runs=1000, deal_mode="reference", restart_finished=True):
+        """One action on every table, entirely on the device: the equity query of every current player
+        (env.py:262-264: 1,000 runs, all players alive), the Monte-Carlo kernels, the agents' decisions
+        (agent_consider_equity / random) and the state machine.  Returns the actions taken (int8 CUDA tensor)."""
+        from .equity import get_equity_batch
+        hole, board, npl, _ = self.queries()
+        out = getattr(self, "_mc_out", None)
+        if out is None:
+            out = {"wins": self.torch.zeros(self.n_tables, dtype=self.torch.int64, device=self.device),
+                   "ties": self.torch.zeros(self.n_tables, dtype=self.torch.int64, device=self.device)}
+            self._mc_out = out
+        out["wins"].zero_(); out["ties"].zero_()
+        get_equity_batch(hole, board, npl, runs, seed_value=(self.seed << 20) + self.decisions, deal_mode=deal_mode,
+                         query_offset=self.table_offset, validate=False, out=out, device=self.device)
+        actions = self.decide(agents, wins=out["wins"], ties=out["ties"], runs=runs)
+        self.step(actions)
+        if restart_finished:
+            self.reset_done()
+        return actions
+
+    # ---- host views ----
+    def state(self):
+        """Host copy of every table as a numpy structured array (dtype TABLE_DTYPE = struct NpkHoldemTable)."""
+        return self.buf.cpu().numpy().view(TABLE_DTYPE)
+
+    @staticmethod
+    def legal_moves_list(mask):
+        return [Action(a) for a in range(10) if int(mask) >> a & 1]

@@ -24,10 +24,12 @@ def _has_gpu():
 
 
 def test_every_declared_symbol_is_exported():
-    header = open(os.path.join(ROOT, "include", "npk.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include")))
+                     if h.endswith(".h"))
     names = set(re.findall(r"\b(npk_[a-z0-9_]+)\s*\(", header))
     assert {"npk_init", "npk_equity_batch", "npk_equity_host", "npk_rank7_batch", "npk_enum_batch",
-            "npk_showdown_batch", "npk_rank7_colex"} <= names
+            "npk_showdown_batch", "npk_rank7_colex", "npk_equity_ranges_batch", "npk_holdem_init", "npk_holdem_step",
+            "npk_holdem_queries", "npk_holdem_decide"} <= names
     L = _lib.lib()
     for n in sorted(names):
         assert hasattr(L, n), n
