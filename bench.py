@@ -43,6 +43,9 @@ def workload(name):
     if name == "cfg4":
         return dict(name="cfg4: 169 starting-hand classes x 1000000 trials, 9 players, preflop", queries=169,
                     trials=1000000, players=9, known=0, shard="trial")
+    if name == "cfg5":
+        return dict(name="cfg5: 65536 six-max HoldemTable self-play steps, get_equity (1000 runs) for every action",
+                    queries=65536, trials=1000, players=6, known=-1, shard="query")
     if name == "cfg1":
         return dict(name="cfg1: AsKs heads-up preflop x 10000 trials", queries=1, trials=10000, players=2, known=0,
                     shard="query")
@@ -187,6 +190,75 @@ def run_reference_arm(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_selfplay(args, wl, rank, world, local_rank, dev, L):
+    """cfg5: every rank owns 65,536 six-max tables (4 equity agents + 2 random ones, main.py:136-150).  One step = one
+    action on every table: equity query of the current player (1,000 runs, all players alive, env.py:262-264) -> Monte-Carlo
+    kernels -> agent decisions -> betting state machine -> finished games restarted; nothing leaves the device."""
+    import torch
+    import torch.distributed as dist
+    from neuron_poker_b200.holdem import EquityAgents, HoldemTables
+    N, runs = wl["queries"], wl["trials"]
+    tb = HoldemTables(N, n_players=6, seed=7, table_offset=rank * N, autoplay=[1] * 6, device=dev)
+    agents = EquityAgents.equity_vs_random()
+    evals = torch.zeros((), dtype=torch.int64, device=dev)
+    acted = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def step(count):
+        tb.selfplay_step(agents, runs=runs, deal_mode=args.deal)
+        if count:
+            _, _, npl, active = tb._q
+            evals.add_((npl.to(torch.int64) * active.to(torch.int64)).sum() * runs)
+            acted.add_(active.to(torch.int64).sum())
+
+    for _ in range(max(args.warmup, 30)):           # reach a steady mix of streets and player counts
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(True)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    tot = torch.stack([evals, acted]).to(torch.float64)
+    if world > 1:
+        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    dev_ms = float(dev_ms.item())
+    st = tb.state()
+    # end to end: the same loop with the actions and rewards of every step copied to the host
+    w0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 50))
+    ev0 = int(evals.item())
+    for _ in range(n_e2e):
+        step(True)
+        tb.rewards.cpu()
+    e2e_s = time.perf_counter() - w0
+    e2e_evals = (int(evals.item()) - ev0) * world
+    line = {
+        "metric": METRIC, "value": float(tot[0].item()) / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 30), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": wl["name"], "tables_per_gpu": N, "runs_per_action": runs, "deal_mode": args.deal,
+                   "agents": "4 x agent_consider_equity + 2 x agent_random (main.py:136-150)",
+                   "table_actions_per_s": float(tot[1].item()) / (dev_ms * 1e-3),
+                   "mean_players_per_query": float(tot[0].item()) / max(1.0, float(tot[1].item()) * runs),
+                   "hands_played_per_table": float(st["hands_played"].mean()), "table_errors": int((st["error"] != 0).sum()),
+                   "l2": "state (50 MB per rank) streams through L2 every step; not flushed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * N,
+                "steps": n_e2e, "api": "HoldemTables.selfplay_step + rewards.cpu()"},
+        "gpu_launches": args.steps * (6 if args.deal == "reference" else 26),
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -219,6 +291,12 @@ def main():
     os.environ["NPK_DEVICE"] = str(local_rank)
     dev = torch.device("cuda", local_rank)
     L = _lib.ensure_init(local_rank)
+
+    if args.workload == "cfg5":
+        run_selfplay(args, wl, rank, world, local_rank, dev, L)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     hole_h, board_h, npl_h = make_queries(wl, world, rank)
     Q, T, P, B = len(hole_h), wl["trials"], wl["players"], wl["known"]
