@@ -304,8 +304,8 @@ def main():
     by_trial = wl["shard"] == "trial" and world > 1
     t_off, t_cnt = npk.dist.trial_shard(T, rank, world) if by_trial else (0, T)
     q_off = 0 if wl["shard"] == "trial" else rank * Q
-    out = {"wins": torch.zeros(Q, dtype=torch.int64, device=dev), "ties": torch.zeros(Q, dtype=torch.int64, device=dev)}
-    both = torch.zeros((Q, 2), dtype=torch.int64, device=dev)
+    both = torch.zeros((2, Q), dtype=torch.int64, device=dev)              # wins row, ties row: one tensor to all-reduce
+    out = {"wins": both[0], "ties": both[1]}
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     # integer-issue peak of this GPU, measured in this run (roofline denominator)
@@ -320,15 +320,14 @@ def main():
 
     def step(i):
         if by_trial:
-            # the kernel accumulates into two contiguous [Q] counters; they are packed into one [Q,2] tensor so a
-            # single all-reduce combines the ranks' trial ranges
-            o = {"wins": out["wins"].zero_(), "ties": out["ties"].zero_()}
+            # the kernel accumulates into the two rows of one [2,Q] tensor; a single all-reduce combines the ranks'
+            # trial ranges
+            both.zero_()
             npk.get_equity_batch(hole, board, npl, t_cnt, seed_value=1000 + i, deal_mode=args.deal, trial_offset=t_off,
-                                 uniform_shape=(P, B), validate=False, out=o)
-            torch.stack([o["wins"], o["ties"]], 1, out=both)
+                                 uniform_shape=(P, B), validate=False, out=out)
             npk.dist.allreduce_counts(both)
         else:
-            out["wins"].zero_(); out["ties"].zero_()
+            both.zero_()
             npk.get_equity_batch(hole, board, npl, T, seed_value=1000 + i, deal_mode=args.deal, query_offset=q_off,
                                  uniform_shape=(P, B), validate=False, out=out)
 
@@ -359,7 +358,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     check_eq = float((out["wins"] + out["ties"]).double().mean().item() / (T if not by_trial else T)) if not by_trial \
-        else float((both[:, 0] + both[:, 1]).double().mean().item() / T)
+        else float((both[0] + both[1]).double().mean().item() / T)
 
     evals_per_step = Q * T * P * (1 if by_trial else world)      # whole job, all ranks
     value = evals_per_step * args.steps / (dev_ms * 1e-3)
@@ -392,7 +391,7 @@ def main():
             npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
         calls = n_calls / (time.perf_counter() - c0)
 
-    kernel_name = "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_reference_kernel"
+    kernel_name = "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_refdeal_kernel<%d,%d>" % (P - 1, 5 - B)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -410,7 +409,7 @@ def main():
         "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if by_trial else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": wl["name"], "queries_per_gpu": Q, "trials": T, "players": P, "known_board_cards": B,
-                   "deal_mode": args.deal, "sharding": ("trial ranges + NCCL all-reduce of [Q,2] counters" if by_trial
+                   "deal_mode": args.deal, "sharding": ("trial ranges + NCCL all-reduce of [2,Q] counters" if by_trial
                                                         else "query blocks, no collective"),
                    "l2": "flushed (256 MiB fill) between timed steps; inputs are 28 KB", "mean_equity": check_eq,
                    "wall_s_timed_loop": wall},

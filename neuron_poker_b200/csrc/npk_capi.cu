@@ -22,11 +22,18 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 
+constexpr int kGroupStreams = 60;   // one per (opponents, known board cards) shape of a mixed batch
+
 struct DeviceState {
     bool ready = false;
     int sm_count = 0;
     npk::DeviceTables t{};
     void* blob = nullptr;
+    // mixed batches: the per-shape kernels run side by side, each on its share of the SMs
+    bool streams_ready = false;
+    cudaStream_t group_stream[kGroupStreams] = {};
+    cudaEvent_t group_done[kGroupStreams] = {};
+    cudaEvent_t fork = nullptr;
 };
 
 npk::Tables g_tables;
@@ -133,13 +140,14 @@ __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, 
     }
 }
 
-// Trials per work item.  Large jobs use 2,048 (64 trials per lane: the per-item set-up -- query load, deck
-// initialisation, reduction -- is then about 2 % of the work); small jobs are cut finer so that a single query still
-// spreads over the whole chip (a lone get_equity call of 10,000 trials becomes 313 one-iteration items).
+// Trials per work item.  Large jobs use up to 2,048 (64 trials per lane: the per-item set-up -- query load, deck
+// initialisation, reduction -- is then about 1 % of the work) but at least eight items per warp, so the last wave of
+// items costs a few per cent at most; small jobs are cut finer so that a single query still spreads over the whole
+// chip (a lone get_equity call of 10,000 trials becomes 313 one-iteration items).
 uint32_t pick_chunk(long long queries, long long trials, int sm_count)
 {
     const long long warps = (long long)sm_count * 16;
-    long long c = (queries * trials) / (4 * warps);
+    long long c = (queries * trials) / (8 * warps);
     if (getenv("NPK_CHUNK")) c = atoll(getenv("NPK_CHUNK"));      // tuning aid
     c = (c + 31) / 32 * 32;
     if (c < 32) c = 32;
@@ -228,6 +236,10 @@ int npk_shutdown(void)
         if (!g_dev[d].ready) continue;
         cudaSetDevice(d);
         cudaFree(g_dev[d].blob);
+        if (g_dev[d].streams_ready) {
+            for (int g = 0; g < kGroupStreams; g++) { cudaStreamDestroy(g_dev[d].group_stream[g]); cudaEventDestroy(g_dev[d].group_done[g]); }
+            cudaEventDestroy(g_dev[d].fork);
+        }
         g_dev[d] = DeviceState{};
     }
     std::lock_guard<std::mutex> lk2(g_host_mu);
@@ -315,7 +327,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
 
     uint32_t counts[64];
     std::memset(counts, 0, sizeof counts);
-    const bool need_classes = !uniform_shape || (flags & NPK_FLAG_VALIDATE);
+    const bool need_classes = !uniform_shape || (flags & NPK_FLAG_VALIDATE);   // both dealers are shape-specialised
     if (need_classes) {
         const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
         classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
@@ -331,13 +343,8 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
             return fail(NPK_ERR_INVALID_ARGUMENT, "queries do not all have the declared uniform shape");
     }
 
-    if (deal_mode == NPK_DEAL_REFERENCE) {
-        // the reference-dealer kernel is generic in players / board size: one launch over all queries
-        p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
-        e = npk::launch_equity_reference(p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
-        if (e != cudaSuccess) return cuda_fail(e, "equity_reference_kernel launch");
-        return NPK_OK;
-    }
+    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+    p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);      // + 15 diagnostic words, all inside the header
 
     const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;   // tuning aid
     if (uniform_shape) {
@@ -354,13 +361,48 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
         classify_fill_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws, go);
     }
+    // One kernel per shape, all running side by side: every shape gets a share of the SMs proportional to its work
+    // (queries x algorithmic instructions per trial), so the launches finish together instead of queueing
+    // twenty under-filled grids one after another.
+    int n_groups = 0;
+    double weight[kGroups], total_weight = 0;
+    for (int g = 0; g < kGroups; g++) {
+        weight[g] = 0;
+        if (!counts[g]) continue;
+        const int players = g / 6 + 1, d = 2 * (players - 1) + (5 - g % 6);
+        weight[g] = (double)counts[g] * (64.0 * ((d + 7) / 8) + 8.0 * d + 15.0 * players + 3.0);
+        total_weight += weight[g];
+        n_groups++;
+    }
+    const bool side_by_side = n_groups > 1 && !getenv("NPK_SERIAL_GROUPS");
+    if (side_by_side && !ds->streams_ready) {
+        for (int g = 0; g < kGroupStreams; g++) {
+            if ((e = cudaStreamCreateWithFlags(&ds->group_stream[g], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+            if ((e = cudaEventCreateWithFlags(&ds->group_done[g], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
+        }
+        if ((e = cudaEventCreateWithFlags(&ds->fork, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
+        ds->streams_ready = true;
+    }
+    if (side_by_side && (e = cudaEventRecord(ds->fork, s)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
     const int32_t* qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
     for (int g = 0; g < kGroups; g++) {
         if (!counts[g]) continue;
         const int nopp = g / 6, known = g % 6;
         p.qindex = qindex + go.off[g]; p.nq = counts[g]; p.work_counter = counters + g;
-        e = npk::launch_equity_uniform(nopp, 5 - known, p, p.nq * chunks, ds->sm_count, forced_warps, s);
+        cudaStream_t gs = s;
+        int sms = ds->sm_count;
+        if (side_by_side) {
+            gs = ds->group_stream[g];
+            sms = (int)(ds->sm_count * weight[g] / total_weight + 0.5);
+            if (sms < 1) sms = 1;
+            if ((e = cudaStreamWaitEvent(gs, ds->fork, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+        }
+        e = npk::launch_equity_uniform(nopp, 5 - known, p, p.nq * chunks, sms, forced_warps, gs);
         if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
+        if (side_by_side) {
+            if ((e = cudaEventRecord(ds->group_done[g], gs)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+            if ((e = cudaStreamWaitEvent(s, ds->group_done[g], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+        }
     }
     return NPK_OK;
 }

@@ -3,8 +3,9 @@
 //   equity_uniform_kernel<NOPP,NB>  K1  batched (query x trial) Monte-Carlo, uniform dealing
 //                                       replaces MonteCarlo.run_montecarlo's loop (reference montecarlo_python.py:210-239)
 //                                       with the C++ sibling's dealing semantics (Montecarlo.cpp:293-312)
-//   equity_reference_kernel         K1' same loop with the Python reference's own (biased) dealer
-//                                       (montecarlo_python.py:165-189) -- see deal_reference() below
+//   equity_refdeal_kernel<NOPP,NB>  K1' same loop with the Python reference's own (biased) dealer
+//                                       (montecarlo_python.py:165-189)
+//   equity_ranges_kernel<MODE>      K1'' generic dealer with opponent / hero ranges and ghost cards
 //   rank7_kernel / rank7_colex      K2  batched 7-card rank ids (hand_evaluator.py:27-119 `_calc_score` ordering)
 //   enum_headsup_kernel             K3  exact heads-up enumeration of opponents and missing board cards
 //   showdown_kernel                 K4  batched get_winner (hand_evaluator.py:9-17)
@@ -227,13 +228,26 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
 }
 
 // =====================================================================================================================
-// K1': the Python reference's dealer (tools/montecarlo_python.py:165-189) on a 52-bit availability mask.
-//   opponent: i1 ~ U[0,n), i2 ~ U[0,n-1), retry while i1 == i2;  c1 = deck.pop(i1); c2 = deck.pop(i2)   (:169-179)
-//             -> c1 = i1-th unseen card in card-id order, c2 = i2-th of the remaining ones
-//   board:    j ~ U[0, n-1)  -> the highest unseen card never reaches the board                            (:188)
-// One Philox word per opponent attempt (i1 from the high product word, i2 from the remainder) and one per board card;
-// words are consumed strictly in order, blocks fetched on demand, so a trial is still a pure function of
-// (seed, query, trial).  Generic in the number of players and known board cards (runtime), one trial per lane.
+// K1': the Python reference's dealer (tools/montecarlo_python.py:165-189), shape-specialised like K1.
+//
+// What the reference does, on the ORDERED list R of unseen cards (n of them):
+//   opponent: i1 ~ U[0,n), i2 ~ U[0,n-1), retry while i1 == i2;  c1 = R.pop(i1); c2 = R.pop(i2)                  (:169-179)
+//   board:    j ~ U[0, n-1);  c = R.pop(j)  -- the highest unseen card never reaches the board                    (:188)
+// Seen as a distribution over cards: (c1, c2) is a uniformly drawn ordered pair of distinct unseen cards, redrawn
+// whenever c2 is the SUCCESSOR of c1 in R (pop(i1) moves R[i1+1] to index i1, so i2 == i1 is exactly that pair; every
+// state has (n-1)^2 admissible pairs and each attempt fails with probability 1/n, which is the distribution of the
+// reference's `passes`); a board card is uniform over R without its maximum.  That needs no ordered list: the cards are
+// drawn from K1's conflict-free shared-memory deck (partial Fisher-Yates, same four shared-memory operations per card),
+// and a 52-bit availability mask in two registers answers "successor of c1" and "maximum of R".  The two excluded
+// outcomes are rare (1/n each), so the retry loops are entered only when some lane of the warp needs them.
+//
+// Random numbers: draw slot s (opponents, then board cards) consumes word s of the Philox4x32-10 stream with counter
+// (trial, query, 0x80000000 + block), key = seed; an opponent's word gives both indices (i1 = hi32(w*n), i2 =
+// hi32(lo32(w*n)*(n-1))).  Retry r = 1, 2, ... of a slot draws from fmix32(w + r * 0x9E3779B9) (the 32-bit murmur3
+// finaliser, a bijection, applied to a counter -- an ITERATED map x -> fmix32(x + c) has fixed points, and one whose
+// indices are (4, 5) of the sorted deck rejects forever: found on the B200 in round 1) instead of a fresh counter block:
+// retries happen in 2 % of the draws, a block per retry would cost more than the rest of the trial.  A trial is still
+// a pure function of (seed, query, trial); a slot that exhausts kMaxRangeAttempts retries raises p.abort_flag.
 // =====================================================================================================================
 struct WordStream {
     uint32_t c0, c1, c2, k0, k1, blk, have;
@@ -263,12 +277,40 @@ __device__ __forceinline__ int select_bit(uint64_t m, int k)
     return base;
 }
 
-__global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const EquityParams p)
+__device__ __forceinline__ uint32_t fmix32(uint32_t x)
 {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+// card id (4*rank + suit) of a descriptor: bits 0..3 hold 12 - rank, bits 4..5 the suit
+__device__ __forceinline__ uint32_t desc_card(uint32_t d) { return 48u - 4u * (d & 15u) + ((d >> 4) & 3u); }
+
+// is card `id2` the lowest unseen card above `id1`?  (avail holds both)
+__device__ __forceinline__ bool is_successor(uint64_t avail, uint32_t id1, uint32_t id2)
+{
+    const uint64_t above = avail >> (id1 + 1u);
+    return above != 0 && id1 + (uint32_t)__ffsll((long long)above) == id2;
+}
+
+template <int NOPP, int NB>
+__global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(const EquityParams p)
+{
+    constexpr int KNOWN = 5 - NB;
+    constexpr int N = 50 - KNOWN;          // unseen cards
+    constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
+    constexpr int NS = NOPP + NB;          // draw slots = Philox words per trial (before retries)
+    constexpr int NBLK = (NS + 3) / 4;
+    static_assert(D <= N, "not enough cards");
+
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
-    const int lane = threadIdx.x & 31;
+    const uint32_t table_bytes = 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + N * 32);
+    uint32_t* fy = scratch + 64 + lane;
+    const uint32_t fy_addr = smem_u32(fy);
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
     const long long n_items = p.nq * chunks;
@@ -276,73 +318,134 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
     for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
         const long long qslot = item / chunks, ci = item - qslot * chunks;
         const long long q = p.qindex ? p.qindex[qslot] : qslot;
-        int known = 0;
-        for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
-        const int nopp = (int)p.n_players[q] - 1;
-        const QueryStatic qs = load_query(p, q, known);
+        const QueryStatic qs = load_query(p, q, KNOWN);
         const uint64_t avail0 = ~qs.known & ((1ull << 52) - 1ull);
-        const int n0 = __popcll(avail0);
+
+        __syncwarp();
+        for (int c = lane; c < 52; c += 32)
+            if (avail0 >> c & 1ull) scratch[__popcll(avail0 & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < N; j++) fy[j * 32] = scratch[j];
+        __syncwarp();
 
         const long long t_begin = ci * p.chunk;
         const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
-        uint32_t wins = 0, ties = 0;
-        unsigned long long passes = 0;
+        uint32_t wins = 0, ties = 0, passes = 0;        // passes <= 64 iterations * 9 opponents * a few attempts
         unsigned long long wt_pack = 0;
 
         for (long long tb = t_begin; tb < t_end; tb += 32) {
             const long long t_local = tb + lane;
             const bool active = t_local < t_end;
             const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
-            WordStream rs;
-            rs.c0 = (uint32_t)trial; rs.c1 = (uint32_t)(trial >> 32); rs.c2 = (uint32_t)q + p.query_offset;
-            rs.k0 = p.seed_lo; rs.k1 = p.seed_hi; rs.blk = 0x80000000u; rs.have = 0;   // stream distinct from K1's
-
+            uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
+#pragma unroll
+            for (int b = 0; b < NBLK; b++)
+                philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, 0x80000000u + (uint32_t)b,
+                              p.seed_lo, p.seed_hi, &w[4 * b]);
+            uint32_t dv[D > 0 ? D : 1], slot[D > 0 ? D : 1];
             uint64_t avail = avail0;
-            int n = n0;
-            uint32_t best = 0;
-            uint32_t oc1[9], oc2[9];
-            if (active) {
-                for (int o = 0; o < nopp; o++) {
-                    uint32_t i1, i2;
-                    do {
-                        const uint64_t prod = (uint64_t)rs.next() * (uint32_t)n;
-                        i1 = (uint32_t)(prod >> 32);
-                        i2 = __umulhi((uint32_t)prod, (uint32_t)(n - 1));
-                        passes++;
-                    } while (i1 == i2);
-                    const int c1 = select_bit(avail, (int)i1);
-                    avail &= ~(1ull << c1);
-                    const int c2 = select_bit(avail, (int)i2);
-                    avail &= ~(1ull << c2);
-                    n -= 2;
-                    oc1[o] = p.tables.desc[c1];
-                    oc2[o] = p.tables.desc[c2];
+            uint32_t tries = 0;
+#pragma unroll
+            for (int o = 0; o < NOPP; o++) {
+                constexpr uint32_t kGold = 0x9E3779B9u;
+                const uint32_t n = (uint32_t)(N - 2 * o);
+                const uint32_t t1 = lds_u32(fy_addr + (n - 1u) * 128u), t2 = lds_u32(fy_addr + (n - 2u) * 128u);
+                const uint32_t w0 = w[o];
+                uint32_t x = w0, i1, i2, c1, c2, id1, id2;
+                bool ok;
+                auto attempt = [&]() {
+                    i1 = __umulhi(x, n);
+                    i2 = __umulhi(x * n, n - 1u);
+                    c1 = lds_u32(fy_addr + i1 * 128u);
+                    const uint32_t other = lds_u32(fy_addr + i2 * 128u);
+                    c2 = i2 == i1 ? t1 : other;               // the hole c1 leaves is filled with the last live card
+                    id1 = desc_card(c1); id2 = desc_card(c2);
+                    ok = !is_successor(avail, id1, id2);
+                    tries++;
+                };
+                attempt();
+                if (__any_sync(0xffffffffu, !ok)) {
+                    uint32_t guard = 0;
+                    while (!ok) {
+                        x = fmix32(w0 + ++guard * kGold);          // retry r draws from fmix32(word + r * golden ratio)
+                        attempt();
+                        if (guard > kMaxRangeAttempts) {         // cannot happen (each attempt fails with probability 1/n)
+                            if (atomicExch(p.abort_flag, 1u) == 0u) {
+                                p.abort_flag[1] = (uint32_t)q; p.abort_flag[2] = (uint32_t)trial; p.abort_flag[3] = (uint32_t)o;
+                                p.abort_flag[4] = x; p.abort_flag[5] = n; p.abort_flag[6] = (uint32_t)avail;
+                                p.abort_flag[7] = (uint32_t)(avail >> 32); p.abort_flag[8] = id1; p.abort_flag[9] = id2;
+                                p.abort_flag[10] = i1; p.abort_flag[11] = i2; p.abort_flag[12] = c1; p.abort_flag[13] = c2;
+                                p.abort_flag[14] = t1; p.abort_flag[15] = t2;
+                            }
+                            break;
+                        }
+                    }
                 }
+                slot[2 * o] = fy_addr + i1 * 128u; slot[2 * o + 1] = fy_addr + i2 * 128u;
+                dv[2 * o] = c1; dv[2 * o + 1] = c2;
+                sts_u32(slot[2 * o], t1);
+                sts_u32(slot[2 * o + 1], i1 == n - 2u ? t1 : t2);
+                avail &= ~((1ull << id1) | (1ull << id2));
             }
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                constexpr uint32_t kGold = 0x9E3779B9u;
+                const uint32_t n = (uint32_t)(N - 2 * NOPP - b);
+                const uint32_t t1 = lds_u32(fy_addr + (n - 1u) * 128u);
+                const uint32_t top = 63u - (uint32_t)__clzll((long long)avail);       // never dealt to the board (:188)
+                const uint32_t w0 = w[NOPP + b];
+                uint32_t x = w0, i1, c1, id1;
+                bool ok;
+                auto attempt = [&]() {
+                    i1 = __umulhi(x, n);
+                    c1 = lds_u32(fy_addr + i1 * 128u);
+                    id1 = desc_card(c1);
+                    ok = id1 != top;
+                };
+                attempt();
+                if (__any_sync(0xffffffffu, !ok)) {
+                    uint32_t guard = 0;
+                    while (!ok) {
+                        x = fmix32(w0 + ++guard * kGold);          // retry r draws from fmix32(word + r * golden ratio)
+                        attempt();
+                        if (guard > kMaxRangeAttempts) {
+                            if (atomicExch(p.abort_flag, 1u) == 0u) {
+                                p.abort_flag[1] = (uint32_t)q; p.abort_flag[2] = (uint32_t)trial; p.abort_flag[3] = 100u + (uint32_t)b;
+                                p.abort_flag[4] = x; p.abort_flag[5] = n; p.abort_flag[6] = (uint32_t)avail;
+                                p.abort_flag[7] = (uint32_t)(avail >> 32); p.abort_flag[8] = id1; p.abort_flag[9] = top;
+                                p.abort_flag[10] = i1; p.abort_flag[12] = c1; p.abort_flag[14] = t1;
+                            }
+                            break;
+                        }
+                    }
+                }
+                slot[2 * NOPP + b] = fy_addr + i1 * 128u;
+                dv[2 * NOPP + b] = c1;
+                sts_u32(slot[2 * NOPP + b], t1);
+                avail &= ~(1ull << id1);
+            }
+#pragma unroll
+            for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[k]);
+            if (active) passes += tries;
+
             uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
-            uint32_t bd[5];
-            int nbd = 0;
-            if (active) {
-                for (int k = known; k < 5; k++) {
-                    const uint32_t j = __umulhi(rs.next(), (uint32_t)(n - 1));
-                    const int c = select_bit(avail, (int)j);
-                    avail &= ~(1ull << c);
-                    n--;
-                    const uint32_t d = p.tables.desc[c];
-                    bd[nbd++] = d;
-                    bsum += d; bcnt += suit_inc(d);
-                }
-            }
+#pragma unroll
+            for (int k = 2 * NOPP; k < D; k++) { bsum += dv[k]; bcnt += suit_inc(dv[k]); }
             const BoardFlush bf = board_flush(bcnt);
             uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
-            for (int k = 0; k < nbd; k++) bfield |= flush_bit(bd[k], bf.fsx);
+#pragma unroll
+            for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[k], bf.fsx);
+
             const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
-            if (active)
-                for (int o = 0; o < nopp; o++)
-                    best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
-                                                 bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
-            // a lone hero (players == 1) is the best of one hand (reference: index 0 of a one-element list)
-            const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
+            uint32_t best = 0;
+#pragma unroll
+            for (int o = 0; o < NOPP; o++) {
+                const uint32_t d0 = dv[2 * o], d1 = dv[2 * o + 1];
+                const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
+                best = max(best, ov);
+            }
+            const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
             wins += win; ties += tie;
             if (p.win_types && (win || tie)) {
                 uint32_t ty = 0;
@@ -351,6 +454,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
                 wt_pack += 1ull << (7 * ty);
             }
         }
+
         wins = __reduce_add_sync(0xffffffffu, wins);
         ties = __reduce_add_sync(0xffffffffu, ties);
         if (lane == 0) {
@@ -358,9 +462,9 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
             atomicAdd(&p.ties[q], (unsigned long long)ties);
         }
         if (p.passes) {
-            // 64-bit warp sum in two halves
-            uint32_t plo = __reduce_add_sync(0xffffffffu, (uint32_t)(passes & 0xffffu));
-            uint32_t phi = __reduce_add_sync(0xffffffffu, (uint32_t)(passes >> 16));
+            // per-lane counts stay below 2^16 per item only in expectation: sum them in two halves
+            const uint32_t plo = __reduce_add_sync(0xffffffffu, passes & 0xffffu);
+            const uint32_t phi = __reduce_add_sync(0xffffffffu, passes >> 16);
             if (lane == 0) atomicAdd(&p.passes[q], (unsigned long long)plo + ((unsigned long long)phi << 16));
         }
         if (p.win_types) {
@@ -381,7 +485,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_reference_kernel(const 
 //       (deck[i1], deck[i2]) -- both read BEFORE anything is popped (:173-174) -- is not allowed.  A hero keeps exactly
 //       those two cards (:146-148); an opponent receives deck.pop(i1) and then deck.pop(i2) from the SHORTENED list
 //       (:178-179), so for i2 >= i1 the tested and the dealt second card differ (reference quirk, kept).
-//       Board card j = hi32(w*(n-1)) (:188).  With a full mask and a fixed hero this is equity_reference_kernel.
+//       Board card j = hi32(w*(n-1)) (:188).  With a full mask and a fixed hero this samples the distribution of K1' (index-based instead of shuffle-based).
 //   UNIFORM (MODE 0): c1 = deck[i1], c2 = (deck without c1)[i2], retry while their class is not allowed; board uniform.
 // One Philox word per attempt, blocks from 0x80000000 (REFERENCE) / 0xC0000000 (UNIFORM).  A draw that needs more than
 // kMaxRangeAttempts attempts raises p.abort_flag; every warp then stops at its next trial (the host reports the error).
@@ -805,7 +909,7 @@ static int uniform_warps(const DeviceTables& t, int nb, int forced)
 template <int NOPP, int NB>
 static cudaError_t launch_uniform_t(const EquityParams& p, long long items, int sm_count, int forced_warps, cudaStream_t s)
 {
-    auto k = equity_uniform_kernel<NOPP, NB>;
+    auto k = p.reference_dealer ? equity_refdeal_kernel<NOPP, NB> : equity_uniform_kernel<NOPP, NB>;
     const int warps = uniform_warps(p.tables, NB, forced_warps);
     const size_t smem = 128 + (size_t)p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes +
                         (size_t)warps * (64 + (45 + NB) * 32) * 4;
@@ -851,15 +955,6 @@ cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long 
 }
 
 size_t aux_smem(const DeviceTables& t) { return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + 256 + 1326 * 2 + 64; }
-
-cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s)
-{
-    size_t smem = aux_smem(p.tables);
-    cudaError_t e = cudaFuncSetAttribute(equity_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    equity_reference_kernel<<<grid, kRefThreads, smem, s>>>(p);
-    return cudaGetLastError();
-}
 
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s)
 {

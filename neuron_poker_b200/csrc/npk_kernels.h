@@ -8,7 +8,7 @@ namespace npk {
 
 constexpr int kEquityMaxThreads = 512; // up to 16 warps per CTA, one CTA per SM (shared memory decides, see uniform_warps)
 constexpr size_t kMaxDynamicSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
-constexpr int kRefThreads = 512;
+constexpr int kRefThreads = 512;       // generic range kernel
 constexpr int kAuxThreads = 512;
 
 struct EquityParams {
@@ -23,6 +23,7 @@ struct EquityParams {
     uint32_t query_offset;        // added to the query number in the Philox counter (sharding queries over GPUs)
     uint32_t seed_lo, seed_hi;
     uint32_t chunk;               // trials per work item
+    uint32_t reference_dealer;    // 0: uniform dealing (K1), 1: the Python reference's dealer (K1')
     unsigned long long* work_counter;
     unsigned long long* wins;     // [Q] hero strictly best
     unsigned long long* ties;     // [Q] hero ties for best
@@ -52,7 +53,6 @@ struct EnumParams {
 size_t aux_smem(const DeviceTables& t);
 cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
                                   cudaStream_t s);
-cudaError_t launch_equity_reference(const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);

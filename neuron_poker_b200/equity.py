@@ -196,7 +196,7 @@ class MonteCarlo(object):
     def run_montecarlo(self, original_player_card_list, original_table_card_list, player_amount, ui, maxRuns,
                        timeout, ghost_cards, opponent_range=1):
         """montecarlo_python.py:191-252.  `ui` and `timeout` are accepted and ignored (every run is executed).
-        The plain case (opponent_range=1, a fixed hero, no ghost cards) runs equity_reference_kernel; anything else runs
+        The plain case (opponent_range=1, a fixed hero, no ghost cards) runs equity_refdeal_kernel; anything else runs
         the range kernel.  A range no remaining hand can satisfy raises NpkError instead of looping forever."""
         if len(original_player_card_list) != 1:
             raise NotImplementedError("exactly one known hand or hero range is supported (the reference's collusion "

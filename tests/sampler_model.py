@@ -7,9 +7,10 @@ checked for bit-identical win / tie / pass / win-type counts -- not only statist
   uniform   (npk_kernels.cu equity_uniform_kernel): partial Fisher-Yates over the unseen cards in ascending card id;
             draw k takes index hi32(x * (N-k)) where x is a fresh Philox word for even k and the low product word of
             the previous draw for odd k; the hole left by a draw is filled with the last live element.
-  reference (equity_reference_kernel): the Python reference's dealer, montecarlo_python.py:165-189, on the ordered
-            list of unseen cards: one word per opponent attempt (i1 = hi32(w*n), i2 = hi32(lo32(w*n)*(n-1)), retry while
-            i1 == i2, pop(i1) then pop(i2)), one word per board card (j = hi32(w*(n-1)), never the last card).
+  reference (equity_refdeal_kernel): the Python reference's dealer, montecarlo_python.py:165-189, as a distribution
+            over cards -- uniform draws from the same deck, redrawn for the two outcomes the reference excludes (second
+            opponent card = successor of the first; board card = highest unseen card); see deal_reference().
+  ranges    (equity_ranges_kernel): the generic index-based dealer with class masks, see deal_ranges().
 """
 M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
 MASK = 0xFFFFFFFF
@@ -62,27 +63,71 @@ class _Words:
         return self.buf.pop(0)
 
 
+GOLD = 0x9E3779B9
+
+
+def fmix32(x):
+    """32-bit murmur3 finaliser (a bijection): the retry stream of equity_refdeal_kernel."""
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & MASK
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & MASK
+    x ^= x >> 16
+    return x
+
+
 def deal_reference(seed, query, trial, hole, board, players):
-    """Returns (opponent hands, full board, passes)."""
+    """equity_refdeal_kernel.  Returns (opponent hands, full board, passes).
+
+    The reference's dealer (montecarlo_python.py:165-189) as a distribution over cards: an opponent gets a uniformly
+    drawn ordered pair of distinct unseen cards, redrawn while the second card is the SUCCESSOR of the first in the
+    ordered list of unseen cards (that is the reference's i1 == i2 retry after pop(i1)); a board card is uniform over
+    the unseen cards without their maximum (randint(0, n-1) never reaches the last list element).
+    Cards come from the same partial Fisher-Yates deck as the uniform dealer; draw slot s uses Philox word s of the
+    stream whose block counter starts at 0x80000000; retry r = 1, 2, ... of a slot draws from fmix32(word + r * 0x9E3779B9)."""
     known = set(hole) | set(board)
     deck = [c for c in range(52) if c not in known]
-    ws = _Words(seed, query, trial)
+    avail = set(deck)
+    nopp, nb = players - 1, 5 - len(board)
+    nblk = (nopp + nb + 3) // 4
+    key = (seed & MASK, (seed >> 32) & MASK)
+    w = []
+    for b in range(nblk):
+        w += philox4x32_10((trial & MASK, (trial >> 32) & MASK, query & MASK, (REFERENCE_BLOCK0 + b) & MASK), key)
+    n = len(deck)
     opp, passes = [], 0
-    for _ in range(players - 1):
-        n = len(deck)
+    for o in range(nopp):
+        x, r = w[o], 0
         while True:
             passes += 1
-            prod = ws.next() * n
+            prod = x * n
             i1, i2 = prod >> 32, ((prod & MASK) * (n - 1)) >> 32
-            if i1 != i2:
+            c1 = deck[i1]
+            c2 = deck[n - 1] if i2 == i1 else deck[i2]
+            above = [c for c in avail if c > c1]
+            if not above or min(above) != c2:
                 break
-        c1 = deck.pop(i1)
-        c2 = deck.pop(i2)
+            r += 1
+            x = fmix32((w[o] + r * GOLD) & MASK)
+        deck[i1] = deck[n - 1]
+        deck[i2] = deck[i1] if i1 == n - 2 else deck[n - 2]       # deck[i1] now holds the old last card
+        avail -= {c1, c2}
+        n -= 2
         opp.append([c1, c2])
     full = list(board)
-    while len(full) < 5:
-        j = (ws.next() * (len(deck) - 1)) >> 32
-        full.append(deck.pop(j))
+    for b in range(nb):
+        x, r = w[nopp + b], 0
+        while True:
+            i1 = (x * n) >> 32
+            c1 = deck[i1]
+            if c1 != max(avail):
+                break
+            r += 1
+            x = fmix32((w[nopp + b] + r * GOLD) & MASK)
+        deck[i1] = deck[n - 1]
+        avail.discard(c1)
+        n -= 1
+        full.append(c1)
     return opp, full, passes
 
 

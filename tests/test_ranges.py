@@ -119,22 +119,26 @@ def test_range_kernels_match_the_sampler_specification(cuda_device):
 
 
 @pytest.mark.gpu
-def test_full_range_reference_mode_equals_the_plain_reference_kernel(cuda_device):
-    """With every class allowed, a fixed hero and no ghost cards the range kernel consumes the same Philox words in the
-    same way as equity_reference_kernel: identical counters."""
+def test_full_range_reference_mode_agrees_with_the_plain_reference_dealer(cuda_device):
+    """With every class allowed, a fixed hero and no ghost cards the range kernel (index-based dealer on the ordered
+    list) and equity_refdeal_kernel (shuffle + rejection of the two excluded outcomes) sample the same distribution:
+    equities within 3 sigma of each other on every query of a mixed batch, mean `passes` per trial equal to 1 %."""
     import neuron_poker_b200 as npk
     rng = np.random.default_rng(3)
-    Q = 24
+    Q, T = 24, 1_000_000
     cards = np.stack([rng.permutation(52)[:7] for _ in range(Q)]).astype(np.uint8)
     hole, board = cards[:, :2].copy(), cards[:, 2:7].copy()
     npl = rng.integers(2, 11, Q).astype(np.uint8)
     for q in range(Q):
         board[q, [0, 3, 4, 5][q % 4]:] = 255
-    a = npk.get_equity_batch(hole, board, npl, 3000, seed_value=9, deal_mode="reference", passes=True, win_types=True)
-    b = npk.get_equity_ranges_batch(hole, board, npl, 3000, opponent_range=1, seed_value=9, deal_mode="reference",
-                                    passes=True, win_types=True)
-    for k in ("wins", "ties", "passes", "win_types"):
-        assert (a[k] == b[k]).all(), k
+    a = npk.get_equity_batch(hole, board, npl, T, seed_value=9, deal_mode="reference", passes=True)
+    b = npk.get_equity_ranges_batch(hole, board, npl, T, opponent_range=1, seed_value=10, deal_mode="reference", passes=True)
+    pa = ((a["wins"] + a["ties"]).double() / T).cpu().numpy()
+    pb = ((b["wins"] + b["ties"]).double() / T).cpu().numpy()
+    se = np.sqrt(np.maximum(pa * (1 - pa), 1e-9) * 2 / T)
+    assert (np.abs(pa - pb) < 3.5 * se + 1e-9).all(), np.max(np.abs(pa - pb) / se)
+    ra, rb = a["passes"].double().cpu().numpy(), b["passes"].double().cpu().numpy()
+    assert (np.abs(ra - rb) < 0.01 * rb).all()
 
 
 @pytest.mark.gpu

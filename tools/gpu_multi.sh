@@ -1,14 +1,18 @@
 #!/bin/bash
-# Multi-GPU session: bench cfg3 (weak, no collective) and cfg4 (strong, NCCL all-reduce) at N ranks.  usage: gpu_multi.sh TAG N
-TAG=${1:-x}; N=${2:-2}; O=gpurun_out; mkdir -p $O
+# Multi-GPU session on one box: bench cfg3 (weak scaling, no collective), cfg4 (strong scaling, NCCL all-reduce inside the
+# step) and cfg5 (self-play, weak) at every N given.   usage: gpu_multi.sh TAG "1 2 4 8"
+TAG=${1:-x}; NS=${2:-"1 2"}; O=gpurun_out; mkdir -p $O
 nvidia-smi -L | head -8
-for WL in cfg3 cfg4; do
-  ST=100; [ $WL = cfg4 ] && ST=20
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-      bench.py --gpus $N --steps $ST --warmup 5 --workload $WL > $O/${TAG}_n${N}_${WL}.json 2> $O/${TAG}_n${N}_${WL}.err
-  echo "rc=$?"; tail -1 $O/${TAG}_n${N}_${WL}.json
-  python bench.py --gpus 1 --steps $ST --warmup 5 --workload $WL --no-cpu-baseline > $O/${TAG}_n1_${WL}.json 2>> $O/${TAG}_n${N}_${WL}.err
-  tail -1 $O/${TAG}_n1_${WL}.json
+for N in $NS; do
+  for WL in cfg3 cfg4 cfg5; do
+    ST=100; [ $WL = cfg4 ] && ST=20
+    EXTRA="--no-cpu-baseline"; [ $WL = cfg5 ] && EXTRA="--deal uniform"
+    if [ $N = 1 ]; then
+      python bench.py --gpus 1 --steps $ST --warmup 5 --workload $WL $EXTRA > $O/${TAG}_n${N}_${WL}.json 2> $O/${TAG}_n${N}_${WL}.err
+    else
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus $N --steps $ST --warmup 5 --workload $WL $EXTRA > $O/${TAG}_n${N}_${WL}.json 2> $O/${TAG}_n${N}_${WL}.err
+    fi
+    echo "N=$N $WL rc=$?"; tail -1 $O/${TAG}_n${N}_${WL}.json | cut -c1-400
+  done
 done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 -m pytest tests/test_dist.py -q -x -k nccl > $O/${TAG}_n${N}_pytest.log 2>&1
-tail -3 $O/${TAG}_n${N}_pytest.log

@@ -4,13 +4,13 @@
 TAG=${1:-x}
 O=gpurun_out
 mkdir -p $O
-python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest.log
+timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 > $O/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/${TAG}_pytest.log
 tail -3 $O/${TAG}_pytest.log
-python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
+timeout 300 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
 cat $O/${TAG}_bench.json
-python bench.py --workload cfg4 --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_cfg4.json 2>> $O/${TAG}_bench.err
+timeout 200 python bench.py --workload cfg4 --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_cfg4.json 2>> $O/${TAG}_bench.err
 cat $O/${TAG}_bench_cfg4.json
-python bench.py --deal reference --steps 20 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_refdeal.json 2>> $O/${TAG}_bench.err
+timeout 200 python bench.py --deal reference --steps 20 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_refdeal.json 2>> $O/${TAG}_bench.err
 cat $O/${TAG}_bench_refdeal.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
