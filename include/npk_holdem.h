@@ -84,9 +84,11 @@ int npk_holdem_init(void* tables, int64_t N, int n_players, double initial_stack
 
 /* env.step(action) for every table: actions [N] int8 on the device, a negative action leaves the table untouched.
  * An action that is not legal costs reward -1 and changes nothing else (env.py:222-226); finished (done) tables and
- * tables stuck in SHOWDOWN at hand start (reference defect) are left untouched.  rewards [N] double or NULL. */
+ * tables stuck in SHOWDOWN at hand start (reference defect) are left untouched.  rewards [N] double or NULL.
+ * restart_finished != 0: a table whose game ends in this step is reset at once (like npk_holdem_reset_done), after its
+ * reward has been recorded. */
 int npk_holdem_step(void* tables, int64_t N, const int8_t* actions, double* rewards, uint64_t seed, int64_t table_offset,
-                    void* stream);
+                    int restart_finished, void* stream);
 
 /* The get_equity arguments of _get_environment for every table: hole [N,2] = cards of the current player (of the
  * winner once the game is over), board [N,5] with 0xFF padding, n_players [N] = sum(player_cycle.alive).

@@ -725,14 +725,14 @@ int npk_holdem_reset_done(void* tables, int64_t N, uint64_t seed, int64_t table_
 }
 
 int npk_holdem_step(void* tables, int64_t N, const int8_t* actions, double* rewards, uint64_t seed, int64_t table_offset,
-                    void* stream)
+                    int restart_finished, void* stream)
 {
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
     if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
     if (!tables || !actions) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
-    cudaError_t e = npk::launch_holdem_step(ds->t, tables, N, actions, rewards, seed, table_offset, static_cast<cudaStream_t>(stream));
+    cudaError_t e = npk::launch_holdem_step(ds->t, tables, N, actions, rewards, seed, table_offset, restart_finished, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_step_kernel launch");
 }
 

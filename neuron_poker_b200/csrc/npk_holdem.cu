@@ -408,23 +408,22 @@ __global__ void holdem_reset_done_kernel(T* tables, long long n, HoldemCtx c0)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !tables[i].done) return;
-    T t = tables[i];
+    T& t = tables[i];                       // in place: only the fields a reset touches travel
     HoldemCtx c = c0;
     c.table_id = c0.table_id + (uint32_t)i;
     t.error = 0;
     table_reset(t, c);
-    tables[i] = t;
 }
 
 // HoldemTable.step for a player that is not an autoplay agent (env.py:170-200)
 __global__ void holdem_step_kernel(T* tables, long long n, const int8_t* __restrict__ actions, double* __restrict__ rewards,
-                                   HoldemCtx c0)
+                                   HoldemCtx c0, int restart_finished)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int action = actions[i];
     if (action < 0) return;
-    T t = tables[i];
+    T& t = tables[i];                       // in place (760 B per table; a step touches a fraction of it)
     if (t.done || t.error) { if (rewards) rewards[i] = 0; return; }
     HoldemCtx c = c0;
     c.table_id = c0.table_id + (uint32_t)i;
@@ -453,7 +452,7 @@ __global__ void holdem_step_kernel(T* tables, long long n, const int8_t* __restr
         }
     }
     if (rewards) rewards[i] = t.reward;
-    tables[i] = t;
+    if (restart_finished && t.done) { t.error = 0; table_reset(t, c); }   // a new env.reset() for a finished game
 }
 
 __global__ void holdem_queries_kernel(const T* __restrict__ tables, long long n, uint8_t* __restrict__ hole,
@@ -546,10 +545,10 @@ cudaError_t launch_holdem_reset_done(const DeviceTables& tab, void* tables, long
 }
 
 cudaError_t launch_holdem_step(const DeviceTables& tab, void* tables, long long n, const int8_t* actions, double* rewards,
-                               uint64_t seed, long long table_offset, cudaStream_t s)
+                               uint64_t seed, long long table_offset, int restart_finished, cudaStream_t s)
 {
     holdem_step_kernel<<<blocks_for(n), kHoldemThreads, 0, s>>>(static_cast<T*>(tables), n, actions, rewards,
-                                                               make_ctx(tab, seed, table_offset));
+                                                               make_ctx(tab, seed, table_offset), restart_finished);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,7 @@ def _bind(L):
     L.npk_holdem_table_bytes.restype = i64
     L.npk_holdem_init.argtypes = [vp, i64, i32, f64, f64, f64, i32, vp, u64, i64, vp]
     L.npk_holdem_reset_done.argtypes = [vp, i64, u64, i64, vp]
-    L.npk_holdem_step.argtypes = [vp, i64, vp, vp, u64, i64, vp]
+    L.npk_holdem_step.argtypes = [vp, i64, vp, vp, u64, i64, i32, vp]
     L.npk_holdem_queries.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.npk_holdem_decide.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, u64, i64, i64, vp, vp]
     if L.npk_holdem_table_bytes() != TABLE_DTYPE.itemsize:
@@ -154,9 +154,10 @@ class HoldemTables(object):
             _lib.check(self.L.npk_holdem_reset_done(self.buf.data_ptr(), self.n_tables, self._u64(self.seed),
                                                     self.table_offset, self._stream()))
 
-    def step(self, actions):
+    def step(self, actions, restart_finished=False):
         """env.step(action) on every table.  `actions`: int8 CUDA tensor, or anything array-like of Action values;
-        negative = leave that table alone.  Returns the rewards tensor [N] (float64, CUDA)."""
+        negative = leave that table alone.  restart_finished: reset a table as soon as its game is over.
+        Returns the rewards tensor [N] (float64, CUDA)."""
         torch = self.torch
         if not isinstance(actions, torch.Tensor):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.int8))
@@ -164,7 +165,8 @@ class HoldemTables(object):
         assert actions.numel() == self.n_tables
         with torch.cuda.device(self.device):
             _lib.check(self.L.npk_holdem_step(self.buf.data_ptr(), self.n_tables, actions.data_ptr(), self.rewards.data_ptr(),
-                                              self._u64(self.seed), self.table_offset, self._stream()))
+                                              self._u64(self.seed), self.table_offset, 1 if restart_finished else 0,
+                                              self._stream()))
         return self.rewards
 
     def queries(self):
@@ -212,9 +214,7 @@ class HoldemTables(object):
         get_equity_batch(hole, board, npl, runs, seed_value=(self.seed << 20) + self.decisions, deal_mode=deal_mode,
                          query_offset=self.table_offset, validate=False, out=out, device=self.device)
         actions = self.decide(agents, wins=out["wins"], ties=out["ties"], runs=runs)
-        self.step(actions)
-        if restart_finished:
-            self.reset_done()
+        self.step(actions, restart_finished=restart_finished)
         return actions
 
     # ---- host views ----
