@@ -13,6 +13,7 @@
 // Everything is integer work on 32-bit lanes: no tensor cores, no floating point.  One trial per lane; the rank
 // tables (about 129 KB) are staged once per CTA into shared memory by the bulk-copy engine and gathered with 16-bit
 // LDS; win / tie counts are reduced with warp REDUX and one 64-bit RED per (warp, work item).
+#include <cstdlib>
 #include "npk_device.cuh"
 #include "npk_kernels.h"
 
@@ -86,7 +87,8 @@ __device__ __forceinline__ uint32_t eval_player(const SmemAddr& a, uint32_t tota
 }
 
 // =====================================================================================================================
-// K1: uniform dealing.  NOPP opponents, NB board cards still to come (known board = 5 - NB), one trial per lane.
+// K1: uniform dealing.  NOPP opponents, NB board cards still to come (known board = 5 - NB), two trials per lane and
+// loop iteration.
 //
 // Dealing = partial Fisher-Yates over the N = 50 - (5 - NB) unseen cards.  Each warp owns a private copy of the deck in
 // shared memory, interleaved so that lane l only ever touches bank l (element j of lane l at word j*32 + l): every
@@ -95,9 +97,14 @@ __device__ __forceinline__ uint32_t eval_player(const SmemAddr& a, uint32_t tota
 // the D overwritten slots are restored in reverse order from registers, which leaves the deck in its canonical order
 // for the next trial: the outcome of a trial depends only on (seed, query, trial), not on how trials are partitioned.
 //
-// Random numbers: Philox4x32-10, counter = (trial_lo, trial_hi, query, block), key = seed.  Each 32-bit word serves two
-// draws by multiply-shift with remainder reuse: x*m -> (index, x'), x'*(m-1) -> index; the first draw of a word is
-// uniform to within 2^-26, the second to within 2^-20 (the remainder takes 2^32/m equally spaced values).
+// Random numbers: Philox4x32-10, key = seed.  Each 32-bit word serves two draws by multiply-shift with remainder reuse:
+// x*m -> (index, x'), x'*(m-1) -> index; the first draw of a word is uniform to within 2^-26, the second to within
+// 2^-20 (the remainder takes 2^32/m equally spaced values).  A trial needs NW = ceil(D/2) words.  Trials are generated
+// in PAIRS so that no word of a block is thrown away: pair P = trial >> 1 draws ceil(2*NW/4) blocks with counter
+// (P_lo, P_hi, query, block), trial 2P reads words [0, NW), trial 2P+1 words [NW, 2*NW).  For the six-player flop
+// (D = 12) that is three blocks per two trials instead of four (-20 instructions per trial, +5.6 % measured), and the
+// two trials of a lane interleave in the instruction stream.  Pairs are numbered by ABSOLUTE trial number
+// (trial_offset included), so the outcome of a trial still depends only on (seed, query, trial).
 // A 64-bit fraction serving six draws (one Philox block for D <= 12) was built and measured in round 1: the two extra
 // multiply-adds per draw cost as much as the half-pruned second block saves, so the 32-bit form stayed.
 // =====================================================================================================================
@@ -116,10 +123,10 @@ template <int NOPP, int NB>
 __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(const EquityParams p)
 {
     constexpr int KNOWN = 5 - NB;
-    constexpr int N = 50 - KNOWN;          // unseen cards
-    constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
-    constexpr int NW = (D + 1) / 2;        // 32-bit words per trial
-    constexpr int NBLK = (NW + 3) / 4;     // Philox blocks per trial
+    constexpr int N = 50 - KNOWN;
+    constexpr int D = 2 * NOPP + NB;
+    constexpr int NW = (D + 1) / 2;
+    constexpr int NBLK2 = (2 * NW + 3) / 4;   // Philox blocks per trial PAIR
     static_assert(D <= N, "not enough cards");
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -127,10 +134,9 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
     const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
     const uint32_t table_bytes = 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per-warp: 64-word scratch (static deck order) + interleaved deck (N rows x 32 lanes)
     uint32_t* scratch = reinterpret_cast<uint32_t*>(smem + table_bytes) + warp * (64 + N * 32);
     uint32_t* fy = scratch + 64 + lane;
-    const uint32_t fy_addr = smem_u32(fy);   // one 32-bit shared address: element j of this lane at fy_addr + 128*j
+    const uint32_t fy_addr = smem_u32(fy);
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
     const long long n_items = p.nq * chunks;
@@ -140,7 +146,6 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
         const long long q = p.qindex ? p.qindex[qslot] : qslot;
         const QueryStatic qs = load_query(p, q, KNOWN);
 
-        // canonical deck: unseen cards in ascending card id.  Lane l places cards l and l+32.
         __syncwarp();
         {
             const uint64_t avail = ~qs.known & ((1ull << 52) - 1ull);
@@ -152,65 +157,64 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
         for (int j = 0; j < N; j++) fy[j * 32] = scratch[j];
         __syncwarp();
 
-        const long long t_begin = ci * p.chunk;
-        const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
+        // absolute trial numbers [a_begin, a_end) of this item; lanes walk over absolute trial PAIRS
+        const unsigned long long a_begin = (unsigned long long)(p.trial_offset + ci * p.chunk);
+        const unsigned long long a_end = (unsigned long long)(p.trial_offset + min(p.trials, (ci + 1) * (long long)p.chunk));
         uint32_t wins = 0, ties = 0;
-        unsigned long long wt_pack = 0;   // nine 7-bit win-type counters (<= 64 iterations per item)
+        unsigned long long wt_pack = 0;
 
-        for (long long tb = t_begin; tb < t_end; tb += 32) {
-            const long long t_local = tb + lane;
-            const bool active = t_local < t_end;
-            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
-            uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
+        for (unsigned long long pb = a_begin >> 1; pb <= (a_end - 1) >> 1; pb += 32) {
+            const unsigned long long pair = pb + lane;
+            uint32_t w[NBLK2 > 0 ? NBLK2 * 4 : 1];
 #pragma unroll
-            for (int b = 0; b < NBLK; b++)
-                philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, (uint32_t)b,
+            for (int b = 0; b < NBLK2; b++)
+                philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)q + p.query_offset, (uint32_t)b,
                               p.seed_lo, p.seed_hi, &w[4 * b]);
-            uint32_t dv[D > 0 ? D : 1], slot[D > 0 ? D : 1];
-            uint32_t rem = 0;
+            uint32_t dv[2][D > 0 ? D : 1];
 #pragma unroll
-            for (int k = 0; k < D; k++) {
-                const uint32_t x = (k & 1) ? rem : w[k >> 1];
-                // index = high word, remainder = low word of x * (N - k).  Written as mul.hi / mul.lo on purpose:
-                // ptxas 12.9 miscompiled the 64-bit form for the last draw (whose low word is dead) into
-                // lo32(x * 4 * (N - k)) -- an out-of-range shared address caught by the per-shape parity test.
-                const uint32_t idx = __umulhi(x, (uint32_t)(N - k));
-                rem = x * (uint32_t)(N - k);
-                slot[k] = fy_addr + idx * 128u;
-                dv[k] = lds_u32(slot[k]);
-                sts_u32(slot[k], lds_u32(fy_addr + (uint32_t)(N - 1 - k) * 128u));
+            for (int u = 0; u < 2; u++) {
+                uint32_t slot[D > 0 ? D : 1];
+                uint32_t rem = 0;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const uint32_t x = (k & 1) ? rem : w[u * NW + (k >> 1)];
+                    const uint32_t idx = __umulhi(x, (uint32_t)(N - k));
+                    rem = x * (uint32_t)(N - k);
+                    slot[k] = fy_addr + idx * 128u;
+                    dv[u][k] = lds_u32(slot[k]);
+                    sts_u32(slot[k], lds_u32(fy_addr + (uint32_t)(N - 1 - k) * 128u));
+                }
+#pragma unroll
+                for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[u][k]);
             }
 #pragma unroll
-            for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[k]);
-
-            // board: descriptor sum, suit counters -> the one suit that can still flush, its rank mask
-            uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
+            for (int u = 0; u < 2; u++) {
+                const unsigned long long trial = 2 * pair + u;
+                const bool active = trial >= a_begin && trial < a_end;
+                uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
 #pragma unroll
-            for (int k = 2 * NOPP; k < D; k++) { bsum += dv[k]; bcnt += suit_inc(dv[k]); }
-            const BoardFlush bf = board_flush(bcnt);
-            uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
+                for (int k = 2 * NOPP; k < D; k++) { bsum += dv[u][k]; bcnt += suit_inc(dv[u][k]); }
+                const BoardFlush bf = board_flush(bcnt);
+                uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
 #pragma unroll
-            for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[k], bf.fsx);
-
-            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
-            uint32_t best = 0;
+                for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[u][k], bf.fsx);
+                const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
+                uint32_t best = 0;
 #pragma unroll
-            for (int o = 0; o < NOPP; o++) {
-                const uint32_t d0 = dv[2 * o], d1 = dv[2 * o + 1];
-                const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
-                best = max(best, ov);
-            }
-            // a lone hero (NOPP == 0) is the best of one hand (reference: index 0 of a one-element list)
-            const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
-            wins += win; ties += tie;
-            if (p.win_types && (win || tie)) {
-                uint32_t ty = 0;
+                for (int o = 0; o < NOPP; o++) {
+                    const uint32_t d0 = dv[u][2 * o], d1 = dv[u][2 * o + 1];
+                    best = max(best, eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr));
+                }
+                const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
+                wins += win; ties += tie;
+                if (p.win_types && (win || tie)) {
+                    uint32_t ty = 0;
 #pragma unroll
-                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
-                wt_pack += 1ull << (7 * ty);
+                    for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                    wt_pack += 1ull << (7 * ty);
+                }
             }
         }
-
         wins = __reduce_add_sync(0xffffffffu, wins);
         ties = __reduce_add_sync(0xffffffffu, ties);
         if (lane == 0) {

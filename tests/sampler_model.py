@@ -6,7 +6,8 @@ checked for bit-identical win / tie / pass / win-type counts -- not only statist
 
   uniform   (npk_kernels.cu equity_uniform_kernel): partial Fisher-Yates over the unseen cards in ascending card id;
             draw k takes index hi32(x * (N-k)) where x is a fresh Philox word for even k and the low product word of
-            the previous draw for odd k; the hole left by a draw is filled with the last live element.
+            the previous draw for odd k; the hole left by a draw is filled with the last live element.  Two consecutive
+            trials share their Philox blocks (see deal_uniform).
   reference (equity_refdeal_kernel): the Python reference's dealer, montecarlo_python.py:165-189, as a distribution
             over cards -- uniform draws from the same deck, redrawn for the two outcomes the reference excludes (second
             opponent card = successor of the first; board card = highest unseen card); see deal_reference().
@@ -28,17 +29,24 @@ def philox4x32_10(ctr, key):
 
 
 def deal_uniform(seed, query, trial, hole, board, players):
-    """Returns (opponent hands [[c1,c2],...], full board [5])."""
+    """equity_uniform_kernel.  Returns (opponent hands [[c1,c2],...], full board [5]).
+
+    A trial needs NW = ceil(D/2) words (two draws per word).  Trials are generated in pairs: pair P = trial >> 1 draws
+    ceil(2*NW/4) Philox blocks with counter (P_lo, P_hi, query, block); trial 2P reads words [0, NW), trial 2P+1 words
+    [NW, 2*NW)."""
     known = set(hole) | set(board)
     deck = [c for c in range(52) if c not in known]
     n = len(deck)
     nopp = players - 1
     d = 2 * nopp + (5 - len(board))
-    nblk = ((d + 1) // 2 + 3) // 4
+    nw = (d + 1) // 2
+    nblk = (2 * nw + 3) // 4
     key = (seed & MASK, (seed >> 32) & MASK)
+    pair, half = trial >> 1, trial & 1
     w = []
     for b in range(nblk):
-        w += philox4x32_10((trial & MASK, (trial >> 32) & MASK, query & MASK, b), key)
+        w += philox4x32_10((pair & MASK, (pair >> 32) & MASK, query & MASK, b), key)
+    w = w[half * nw:(half + 1) * nw]
     out, rem = [], 0
     for k in range(d):
         x = rem if k & 1 else w[k >> 1]

@@ -1,6 +1,6 @@
 #!/bin/bash
 # usage: tools/sass_loop.sh NOPP NB  -> opcode histogram of the kernel's innermost trial loop (backward branch span)
-K="_ZN3npk21equity_uniform_kernelILi${1}ELi${2}EEEvNS_12EquityParamsE"
+K="_ZN3npk${3:-21equity_uniform_kernel}ILi${1}ELi${2}EEEvNS_12EquityParamsE"
 cuobjdump -sass -fun "$K" neuron_poker_b200/libnpk.so | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*([0-9a-f]{4})\*\/\s+/\1 /; s/\s*\/\*.*//' > /tmp/k.txt
 python3 - <<'PY'
 import re,collections
