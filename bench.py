@@ -43,6 +43,9 @@ def workload(name):
     if name == "cfg4":
         return dict(name="cfg4: 169 starting-hand classes x 1000000 trials, 9 players, preflop", queries=169,
                     trials=1000000, players=9, known=0, shard="trial")
+    if name == "cfg2":
+        return dict(name="cfg2: exact enumeration of 4096 heads-up turn spots + 4096 river spots; rank ids of 64 M hands",
+                    queries=4096, trials=0, players=2, known=4, shard="query")
     if name == "cfg5":
         return dict(name="cfg5: 65536 six-max HoldemTable self-play steps, get_equity (1000 runs) for every action",
                     queries=65536, trials=1000, players=6, known=-1, shard="query")
@@ -190,6 +193,80 @@ def run_reference_arm(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_exact(args, wl, rank, world, local_rank, dev):
+    """cfg2: the exact kernels.  K3 enumerates every opponent hand x board completion of 4,096 heads-up turn
+    spots and 4,096 river spots (seed-0 synthetic: 2 hole + 4 / 5 board cards, distinct, uniform); K2 ranks 64 M random
+    7-card hands (7 B in, 2 B out per hand).  value = showdown evals/s of the enumeration (two hands per matchup)."""
+    import torch
+    import torch.distributed as dist
+    import neuron_poker_b200 as npk
+    Q = wl["queries"]
+    g = torch.Generator().manual_seed(rank)
+    cards = torch.rand(2 * Q, 52, generator=g).argsort(1)[:, :7].to(torch.uint8)
+    hole = cards[:, :2].contiguous().to(dev)
+    board = cards[:, 2:7].clone()
+    board[:Q, 4] = 255                                      # first half: turn spots (one card to come)
+    board = board.to(dev)
+    npl = torch.full((2 * Q,), 2, dtype=torch.uint8, device=dev)
+    matchups = Q * 46 * (45 * 44 // 2) + Q * (45 * 44 // 2)  # turn: 46 rivers x C(45,2) opponent hands; river: C(45,2)
+    n_hands = 64 << 20
+    hands = torch.rand(1 << 20, 52, generator=g).argsort(1)[:, :7].to(torch.uint8).to(dev).repeat(64, 1).contiguous()
+    for _ in range(max(3, args.warmup)):
+        w, t, l = npk.enumerate_equity(hole, board, npl)
+        r = npk.rank7(hands)
+    torch.cuda.synchronize()
+    assert int((w + t + l).sum().item()) == matchups
+    if world > 1:
+        dist.barrier()
+    steps = min(args.steps, 50)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev[0].record()
+    for _ in range(steps):
+        npk.enumerate_equity(hole, board, npl)
+    ev[1].record()
+    for _ in range(steps):
+        npk.rank7(hands)
+    ev[2].record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    enum_ms, rank_ms = (float(x) / steps for x in ms.tolist())
+    # end to end: host arrays in, host arrays out
+    hole_h, board_h, npl_h = hole.cpu().numpy(), board.cpu().numpy(), npl.cpu().numpy()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        w, t, l = npk.enumerate_equity(hole_h, board_h, npl_h)
+        w.cpu(); t.cpu(); l.cpu()
+    e2e_s = (time.perf_counter() - t0) / 3
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6544.3))
+    rank_gbs = n_hands * 9 / (rank_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": 2 * matchups * world / (enum_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, args.warmup), "ms_per_step": enum_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": wl["name"], "spots_per_gpu": 2 * Q, "matchups_per_step": matchups,
+                       "matchups_per_s": matchups * world / (enum_ms * 1e-3), "rank7_hands_per_s": n_hands * world / (rank_ms * 1e-3),
+                       "rank7_ms": rank_ms, "l2": "rank7 input 448 MiB > L2; enumeration inputs are 64 KB"},
+            "clocks": clocks,
+            "e2e": {"value": 2 * matchups * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 16 * Q, "d2h_bytes_per_step": 48 * Q,
+                    "steps": 3, "api": "neuron_poker_b200.enumerate_equity (numpy in, counters read back)"},
+            "gpu_launches": 2 * steps,
+            "roofline": {"bound": "hbm", "kernel": "rank7_kernel", "achieved": rank_gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": rank_gbs / hbm, "traffic": None,
+                         "algorithmic_bytes_per_hand": 9, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.3"}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 def run_selfplay(args, wl, rank, world, local_rank, dev, L):
     """cfg5: every rank owns 65,536 six-max tables (4 equity agents + 2 random ones, main.py:136-150).  One step = one
     action on every table: equity query of the current player (1,000 runs, all players alive, env.py:262-264) -> Monte-Carlo
@@ -292,6 +369,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     L = _lib.ensure_init(local_rank)
 
+    if args.workload == "cfg2":
+        run_exact(args, wl, rank, world, local_rank, dev)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "cfg5":
         run_selfplay(args, wl, rank, world, local_rank, dev, L)
         if world > 1:

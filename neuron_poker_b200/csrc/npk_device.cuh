@@ -176,24 +176,24 @@ __device__ __forceinline__ uint32_t suit_inc(uint32_t d) { return 1u << ((d >> 2
 __device__ __forceinline__ uint32_t field_selector(uint32_t fs) { return 0x9910u + fs * 0x2222u; }
 
 // Plain 7-card evaluation from card descriptors (rank7 / showdown / enumeration kernels; the Monte-Carlo loops carry the
-// board part across players instead).
+// board part across players instead).  Per card: one add into the key sum and one into the nibble-per-suit counters;
+// the flush suit's rank mask is only assembled for the few hands that hold five cards of a suit.
 __device__ __forceinline__ uint32_t eval7_desc(const SmemAddr& a, const uint32_t d[7])
 {
-    uint32_t total = 0, lo = 0, hi = 0, cnt = 0x3333u;
+    uint32_t total = 0, cnt = 0x3333u;
 #pragma unroll
     for (int i = 0; i < 7; i++) {
-        uint32_t l, h;
-        card_bits(d[i], l, h);
         total += d[i];
-        lo |= l;
-        hi |= h;
         cnt += suit_inc(d[i]);
     }
     uint32_t v = lookup_nonflush(a, total);
     const uint32_t f = cnt & 0x8888u;                 // nibble >= 8  <=>  that suit holds >= 5 cards
     if (f) {
-        const uint32_t fs = ((31u - __clz(f)) >> 2) & 3u;
-        v = lds_u16(a.flush + 2u * prmt(lo, hi, field_selector(fs)));   // a flush excludes full house / quads in 7 cards
+        const uint32_t fsx = (((31u - __clz(f)) >> 2) & 3u) << 4;
+        uint32_t field = 0;
+#pragma unroll
+        for (int i = 0; i < 7; i++) field |= shr_clamp(0x1000u, (d[i] ^ fsx) & 63u);
+        v = lds_u16(a.flush + 2u * field);            // a flush excludes full house / quads in 7 cards
     }
     return v;
 }

@@ -645,19 +645,62 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
 // =====================================================================================================================
 // K2: rank ids of 7-card hands
 // =====================================================================================================================
+// Four consecutive hands per thread: their 28 bytes are seven aligned 32-bit words (a warp reads 896 contiguous bytes),
+// all seven loads are issued before the first use, and the four rank ids leave as one 8-byte store.  HBM traffic is the
+// algorithmic 9 B per hand; the per-card work is one byte extract, one descriptor gather from shared memory, one add into
+// the key sum and the suit-counter update.
 __global__ void __launch_bounds__(kAuxThreads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
                                                                long long n, uint16_t* __restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
-    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
-    if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
+    // descriptor of a card = per-rank word | suit << 4: the 13 per-rank words sit in 13 different banks, so this gather
+    // never conflicts (lanes with the same rank read the same word), unlike a 52-entry per-card table
+    uint32_t* s_rank = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
+    if (threadIdx.x < 13) s_rank[threadIdx.x] = tables.desc[4 * threadIdx.x];          // suit 0 of each rank
     __syncthreads();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    auto card_desc = [&](uint32_t card) { return s_rank[card >> 2] | ((card & 3u) << 4); };
+    const bool aligned = ((reinterpret_cast<uintptr_t>(cards) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
+    const long long quads = aligned ? n / 4 : 0;
+    const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(cards);
+    // software pipeline: the seven words of the NEXT quad are in flight while this one is evaluated (one CTA of 16 warps
+    // per SM cannot hide HBM latency by occupancy alone)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nxt[7];
+    if (g < quads) {
+#pragma unroll
+        for (int k = 0; k < 7; k++) nxt[k] = __ldg(words + 7 * g + k);
+    }
+    for (; g < quads; g += stride) {
+        uint32_t w[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) w[k] = nxt[k];
+        if (g + stride < quads) {
+#pragma unroll
+            for (int k = 0; k < 7; k++) nxt[k] = __ldg(words + 7 * (g + stride) + k);
+        }
+        uint32_t r[4];
+#pragma unroll
+        for (int h = 0; h < 4; h++) {
+            uint32_t d[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                const int byte = 7 * h + k;
+                d[k] = card_desc((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
+            }
+            r[h] = eval7_desc(st, d);
+        }
+        uint2 packed;
+        packed.x = r[0] | (r[1] << 16);
+        packed.y = r[2] | (r[3] << 16);
+        *reinterpret_cast<uint2*>(out + 4 * g) = packed;
+    }
+    for (long long i = 4 * quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         uint32_t d[7];
 #pragma unroll
-        for (int k = 0; k < 7; k++) d[k] = s_desc[cards[7 * i + k]];
+        for (int k = 0; k < 7; k++) d[k] = card_desc(cards[7 * i + k]);
         out[i] = (uint16_t)eval7_desc(st, d);
     }
 }
@@ -701,50 +744,90 @@ __global__ void __launch_bounds__(kAuxThreads, 1) rank7_colex_kernel(const Devic
 // unseen cards.  Also ordered pairs of disjoint opponent hands on a complete board (three players, river).
 // Outputs win / tie / lose from the hero's point of view (hero > / == / < best opponent).
 // =====================================================================================================================
+// Fast paths (at most two board cards to come, one opponent): a warp takes one board completion, computes the board part
+// and the hero's value once, and its lanes walk over the opponent pairs -- per matchup one 3-input add, the table
+// gathers and the flush test, exactly the per-player work of the Monte-Carlo kernels.  The list of pairs (a < b) of
+// unseen cards is built once per query in shared memory and doubles as the list of two-card completions.
 __global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
     uint8_t* extra = smem + 128 + p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes;
-    uint32_t* s_deck = reinterpret_cast<uint32_t*>(extra);            // [52] descriptors of unseen cards
-    uint16_t* s_pairval = reinterpret_cast<uint16_t*>(extra + 256);   // [1326] rank of each opponent pair (river)
+    uint32_t* s_deck = reinterpret_cast<uint32_t*>(extra);            // [52] descriptors of unseen cards, ascending id
+    uint16_t* s_pairval = reinterpret_cast<uint16_t*>(extra + 256);   // [1326] rank of each opponent pair (3 players, river)
+    uint16_t* s_pair = reinterpret_cast<uint16_t*>(extra + 256 + 2688);   // [1326] a | b << 8, a < b
     __shared__ unsigned long long s_acc[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     for (long long q = blockIdx.x; q < p.nq; q += gridDim.x) {
         int known = 0;
         for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
         const int nopp = (int)p.n_players[q] - 1;
-        // static parts (recomputed per thread; cheap)
         uint64_t knownmask = (1ull << p.hole[2 * q]) | (1ull << p.hole[2 * q + 1]);
-        uint32_t hd[2] = {p.tables.desc[p.hole[2 * q]], p.tables.desc[p.hole[2 * q + 1]]};
+        const uint32_t hd[2] = {p.tables.desc[p.hole[2 * q]], p.tables.desc[p.hole[2 * q + 1]]};
         uint32_t bd[5];
         for (int i = 0; i < known; i++) { bd[i] = p.tables.desc[p.board[5 * q + i]]; knownmask |= 1ull << p.board[5 * q + i]; }
         const uint64_t avail = ~knownmask & ((1ull << 52) - 1ull);
         const int n = __popcll(avail);
+        const int npairs = n * (n - 1) / 2;
         __syncthreads();
         if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
         for (int c = threadIdx.x; c < 52; c += blockDim.x)
             if (avail >> c & 1ull) s_deck[__popcll(avail & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        for (int b = threadIdx.x; b < n; b += blockDim.x)                // pair index C(b,2) + a
+            for (int a = 0; a < b; a++) s_pair[b * (b - 1) / 2 + a] = (uint16_t)(a | b << 8);
         __syncthreads();
 
         unsigned long long win = 0, tie = 0, lose = 0;
         const int missing = 5 - known;
-        if (nopp == 1) {
-            // completions: combinations of `missing` cards out of n, by colex index; pairs: (a < b) out of n
+        if (nopp == 1 && missing <= 2) {
+            const int ncomp = missing == 0 ? 1 : (missing == 1 ? n : npairs);
+            const int wpc = ncomp >= nwarps ? 1 : nwarps / ncomp;        // warps sharing one completion
+            const int groups = nwarps / wpc;
+            uint32_t ksum = 0, kcnt = 0x5555u, klo = 0, khi = 0;           // known board: sum, suit counters, suit-major masks
+            for (int i = 0; i < known; i++) {
+                uint32_t l, h;
+                card_bits(bd[i], l, h);
+                ksum += bd[i]; kcnt += suit_inc(bd[i]); klo |= l; khi |= h;
+            }
+            uint32_t hlo, hhi, l, h;
+            card_bits(hd[0], hlo, hhi);
+            card_bits(hd[1], l, h);
+            hlo |= l; hhi |= h;
+            if (warp < groups * wpc) {
+                for (int ic = warp / wpc; ic < ncomp; ic += groups) {
+                    int c0 = -1, c1 = -1;
+                    if (missing == 1) c0 = ic;
+                    else if (missing == 2) { const uint32_t pr = s_pair[ic]; c0 = pr & 255; c1 = pr >> 8; }
+                    const uint32_t e0 = c0 >= 0 ? s_deck[c0] : 0u, e1 = c1 >= 0 ? s_deck[c1] : 0u;
+                    uint32_t bsum = ksum + e0 + e1, bcnt = kcnt;
+                    if (c0 >= 0) bcnt += suit_inc(e0);
+                    if (c1 >= 0) bcnt += suit_inc(e1);
+                    const BoardFlush bf = board_flush(bcnt);
+                    uint32_t bfield = prmt(klo, khi, bf.sel);
+                    if (c0 >= 0) bfield |= flush_bit(e0, bf.fsx);
+                    if (c1 >= 0) bfield |= flush_bit(e1, bf.fsx);
+                    const uint32_t hv = eval_player(st, bsum + hd[0] + hd[1], bfield | prmt(hlo, hhi, bf.sel), bf.thr);
+                    for (int ip = (warp % wpc) * 32 + lane; ip < npairs; ip += 32 * wpc) {
+                        const uint32_t pr = s_pair[ip];
+                        const int a = pr & 255, b = pr >> 8;
+                        if (a == c0 || a == c1 || b == c0 || b == c1) continue;
+                        const uint32_t d0 = s_deck[a], d1 = s_deck[b];
+                        const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
+                        win += hv > ov; tie += hv == ov; lose += hv < ov;
+                    }
+                }
+            }
+        } else if (nopp == 1) {
+            // three or more board cards to come: generic walk over (completion, pair) by colexicographic unranking
             long long ncomp = 1;
             for (int i = 0; i < missing; i++) ncomp = ncomp * (n - i) / (i + 1);
-            const long long npairs = (long long)n * (n - 1) / 2;
             const long long total = ncomp * npairs;
             for (long long w = threadIdx.x; w < total; w += blockDim.x) {
                 const long long ic = w / npairs;
-                long long ip = w - ic * npairs;
-                // unrank pair (a < b): ip = C(b,2) + a
-                int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)ip)) * 0.5);
-                while ((long long)b * (b - 1) / 2 > ip) b--;
-                while ((long long)(b + 1) * b / 2 <= ip) b++;
-                const int a = (int)(ip - (long long)b * (b - 1) / 2);
-                // unrank completion
+                const uint32_t pr = s_pair[(int)(w - ic * npairs)];
+                const int a = pr & 255, b = pr >> 8;
                 int comp[5];
                 {
                     unsigned long long r = (unsigned long long)ic;
@@ -768,32 +851,26 @@ __global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p
                 win += hv > ov; tie += hv == ov; lose += hv < ov;
             }
         } else if (nopp == 2 && known == 5) {
-            const int npairs = n * (n - 1) / 2;
             uint32_t h7[7] = {hd[0], hd[1], bd[0], bd[1], bd[2], bd[3], bd[4]};
             const uint32_t hv = eval7_desc(st, h7);
             for (int ip = threadIdx.x; ip < npairs; ip += blockDim.x) {
-                int b = (int)((1.0 + sqrt(1.0 + 8.0 * (double)ip)) * 0.5);
-                while (b * (b - 1) / 2 > ip) b--;
-                while ((b + 1) * b / 2 <= ip) b++;
-                const int a = ip - b * (b - 1) / 2;
-                uint32_t o7[7] = {s_deck[a], s_deck[b], bd[0], bd[1], bd[2], bd[3], bd[4]};
+                const uint32_t pr = s_pair[ip];
+                uint32_t o7[7] = {s_deck[pr & 255], s_deck[pr >> 8], bd[0], bd[1], bd[2], bd[3], bd[4]};
                 s_pairval[ip] = (uint16_t)eval7_desc(st, o7);
             }
             __syncthreads();
-            const long long total = (long long)npairs * npairs;
-            for (long long w = threadIdx.x; w < total; w += blockDim.x) {
-                const int i1 = (int)(w / npairs), i2 = (int)(w - (long long)i1 * npairs);
-                int b1 = (int)((1.0 + sqrt(1.0 + 8.0 * (double)i1)) * 0.5);
-                while (b1 * (b1 - 1) / 2 > i1) b1--;
-                while ((b1 + 1) * b1 / 2 <= i1) b1++;
-                const int a1 = i1 - b1 * (b1 - 1) / 2;
-                int b2 = (int)((1.0 + sqrt(1.0 + 8.0 * (double)i2)) * 0.5);
-                while (b2 * (b2 - 1) / 2 > i2) b2--;
-                while ((b2 + 1) * b2 / 2 <= i2) b2++;
-                const int a2 = i2 - b2 * (b2 - 1) / 2;
-                if (a1 == a2 || a1 == b2 || b1 == a2 || b1 == b2) continue;
-                const uint32_t best = max((uint32_t)s_pairval[i1], (uint32_t)s_pairval[i2]);
-                win += hv > best; tie += hv == best; lose += hv < best;
+            // ordered pairs of disjoint opponent hands: warp-strided first hand, lane-strided second hand
+            for (int i1 = warp; i1 < npairs; i1 += nwarps) {
+                const uint32_t p1 = s_pair[i1];
+                const int a1 = p1 & 255, b1 = p1 >> 8;
+                const uint32_t v1 = s_pairval[i1];
+                for (int i2 = lane; i2 < npairs; i2 += 32) {
+                    const uint32_t p2 = s_pair[i2];
+                    const int a2 = p2 & 255, b2 = p2 >> 8;
+                    if (a1 == a2 || a1 == b2 || b1 == a2 || b1 == b2) continue;
+                    const uint32_t best = max(v1, (uint32_t)s_pairval[i2]);
+                    win += hv > best; tie += hv == best; lose += hv < best;
+                }
             }
         }
         // block reduction: warp shuffles then one shared atomic per warp
@@ -958,7 +1035,7 @@ cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long 
     }
 }
 
-size_t aux_smem(const DeviceTables& t) { return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + 256 + 1326 * 2 + 64; }
+size_t aux_smem(const DeviceTables& t) { return 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + 256 + 2 * 2688 + 64; }
 
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s)
 {
