@@ -29,6 +29,10 @@ struct DeviceState {
     int sm_count = 0;
     npk::DeviceTables t{};
     void* blob = nullptr;
+    // one-query blocking calls (npk_equity_host, Q == 1): counters in device memory, results in mapped host memory
+    npk::SingleCall* single = nullptr;
+    npk::SingleResult* single_host = nullptr;
+    cudaStream_t single_stream = nullptr;
     // mixed batches: the per-shape kernels run side by side, each on its share of the SMs
     bool streams_ready = false;
     cudaStream_t group_stream[kGroupStreams] = {};
@@ -144,13 +148,13 @@ __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, 
 // initialisation, reduction -- is then about 1 % of the work) but at least eight items per warp, so the last wave of
 // items costs a few per cent at most; small jobs are cut finer so that a single query still spreads over the whole
 // chip (a lone get_equity call of 10,000 trials becomes 313 one-iteration items).
-uint32_t pick_chunk(long long queries, long long trials, int sm_count)
+uint32_t pick_chunk(long long queries, long long trials, int sm_count, int lanes_worth = 32)
 {
     const long long warps = (long long)sm_count * 16;
     long long c = (queries * trials) / (8 * warps);
     if (getenv("NPK_CHUNK")) c = atoll(getenv("NPK_CHUNK"));      // tuning aid
-    c = (c + 31) / 32 * 32;
-    if (c < 32) c = 32;
+    c = (c + lanes_worth - 1) / lanes_worth * lanes_worth;      // a warp iteration covers 32 trials (K1': one per lane) or 64 (K1: a pair per lane)
+    if (c < lanes_worth) c = lanes_worth;
     if (c > 2048) c = 2048;
     if (trials <= c) return (uint32_t)(trials > 0 ? trials : 1);
     return (uint32_t)c;
@@ -236,6 +240,9 @@ int npk_shutdown(void)
         if (!g_dev[d].ready) continue;
         cudaSetDevice(d);
         cudaFree(g_dev[d].blob);
+        if (g_dev[d].single) {
+            cudaFree(g_dev[d].single); cudaFreeHost(g_dev[d].single_host); cudaStreamDestroy(g_dev[d].single_stream);
+        }
         if (g_dev[d].streams_ready) {
             for (int g = 0; g < kGroupStreams; g++) { cudaStreamDestroy(g_dev[d].group_stream[g]); cudaEventDestroy(g_dev[d].group_done[g]); }
             cudaEventDestroy(g_dev[d].fork);
@@ -317,7 +324,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
@@ -419,8 +426,70 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_host_mu);
-    HostStage& st = g_stage;
     cudaError_t e;
+    if (Q == 1 && !getenv("NPK_NO_SINGLE_PATH")) {
+        // One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in
+        // device memory between calls (the last warp hands them over and zeroes them), the result lands in mapped host
+        // memory.  No H2D / D2H copy, no memset.
+        unsigned long long mask = 0;
+        int known = 0;
+        bool ended = false, bad = n_players[0] < 1 || n_players[0] > 10;
+        for (int i = 0; i < 2 && !bad; i++) {
+            const int c = hole[i];
+            if (c >= 52 || (mask >> c & 1ull)) bad = true; else mask |= 1ull << c;
+        }
+        for (int i = 0; i < 5 && !bad; i++) {
+            const int c = board[i];
+            if (c == 0xFF) { ended = true; continue; }
+            if (ended || c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
+            mask |= 1ull << c;
+            known++;
+        }
+        if (bad) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+        if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+            return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+        if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+        if (!ds->single) {
+            if ((e = cudaStreamCreateWithFlags(&ds->single_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+            if ((e = cudaHostAlloc(&ds->single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+            npk::SingleResult* dptr = nullptr;
+            if ((e = cudaHostGetDevicePointer(&dptr, ds->single_host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+            if ((e = cudaMalloc(&ds->single, sizeof(npk::SingleCall))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+            npk::SingleCall init{};
+            init.host = dptr;
+            if ((e = cudaMemcpy(ds->single, &init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+        }
+        wins_strict[0] = 0; ties[0] = 0;
+        if (win_types) std::memset(win_types, 0, 72);
+        if (passes) passes[0] = 0;
+        if (trials == 0) return NPK_OK;
+        npk::EquityParams p{};
+        p.tables = ds->t;
+        p.hole = nullptr; p.board = nullptr; p.n_players = nullptr; p.qindex = nullptr;
+        p.inline_query = (uint64_t)hole[0] | (uint64_t)hole[1] << 8;
+        for (int i = 0; i < 5; i++) p.inline_query |= (uint64_t)board[i] << (16 + 8 * i);
+        p.nq = 1; p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
+        p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+        p.chunk = pick_chunk(1, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
+        p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+        p.single = ds->single;
+        p.work_counter = &ds->single->work_counter;
+        p.wins = &ds->single->wins; p.ties = &ds->single->ties;
+        p.win_types = win_types ? ds->single->win_types : nullptr;
+        p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &ds->single->passes : nullptr;
+        p.abort_flag = ds->single->abort_flag;
+        const long long chunks = (trials + p.chunk - 1) / p.chunk;
+        const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;
+        e = npk::launch_equity_uniform(n_players[0] - 1, 5 - known, p, chunks, ds->sm_count, forced_warps, ds->single_stream);
+        if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
+        if ((e = cudaStreamSynchronize(ds->single_stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
+        const npk::SingleResult* r = ds->single_host;
+        wins_strict[0] = r->wins; ties[0] = r->ties;
+        if (win_types) for (int i = 0; i < 9; i++) win_types[i] = r->win_types[i];
+        if (passes) passes[0] = r->passes;
+        return NPK_OK;
+    }
+    HostStage& st = g_stage;
     if (st.device != dev || st.cap_q < Q) {
         if (st.device >= 0) {
             cudaSetDevice(st.device);

@@ -42,7 +42,8 @@ struct QueryStatic {
 __device__ __forceinline__ QueryStatic load_query(const EquityParams& p, long long q, int nb_known)
 {
     QueryStatic s;
-    const uint8_t h0 = p.hole[2 * q], h1 = p.hole[2 * q + 1];
+    const uint8_t h0 = p.hole ? p.hole[2 * q] : (uint8_t)p.inline_query;
+    const uint8_t h1 = p.hole ? p.hole[2 * q + 1] : (uint8_t)(p.inline_query >> 8);
     uint32_t d0 = p.tables.desc[h0], d1 = p.tables.desc[h1], l, h;
     s.hero_sum = d0 + d1;
     card_bits(d0, s.hero_lo, s.hero_hi);
@@ -51,13 +52,37 @@ __device__ __forceinline__ QueryStatic load_query(const EquityParams& p, long lo
     s.known = (1ull << h0) | (1ull << h1);
     s.board_sum = 0; s.board_lo = 0; s.board_hi = 0; s.board_cnt = 0x5555u;
     for (int i = 0; i < nb_known; i++) {
-        const uint8_t c = p.board[5 * q + i];
+        const uint8_t c = p.hole ? p.board[5 * q + i] : (uint8_t)(p.inline_query >> (16 + 8 * i));
         uint32_t d = p.tables.desc[c];
         card_bits(d, l, h);
         s.board_sum += d; s.board_lo |= l; s.board_hi |= h; s.board_cnt += suit_inc(d);
         s.known |= 1ull << c;
     }
     return s;
+}
+
+// One-query fast path: the last warp of the grid to get here hands the counters to the host and resets them.
+__device__ __forceinline__ void finish_single_call(const EquityParams& p, int lane)
+{
+    SingleCall* sc = p.single;
+    if (!sc) return;
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+        __threadfence();                                              // this warp's atomics before its ticket
+        const unsigned int total = gridDim.x * (blockDim.x >> 5);
+        last = atomicAdd(&sc->ticket, 1u) == total - 1u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    if (lane < 12) {
+        unsigned long long* src = &sc->wins;                           // wins, ties, win_types[9], passes are contiguous
+        const unsigned long long v = atomicExch(src + lane, 0ull);    // read and reset for the next call
+        (&sc->host->wins)[lane] = v;
+    }
+    if (lane == 0) { sc->work_counter = 0; sc->ticket = 0; }
+    __threadfence_system();
 }
 
 // What a complete board says about flushes: at most one suit (the one holding >= 3 board cards) can still flush.
@@ -229,6 +254,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
             }
         }
     }
+    finish_single_call(p, lane);
 }
 
 // =====================================================================================================================
@@ -479,6 +505,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
             }
         }
     }
+    finish_single_call(p, lane);
 }
 
 // =====================================================================================================================

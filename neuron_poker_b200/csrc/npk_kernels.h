@@ -11,6 +11,20 @@ constexpr size_t kMaxDynamicSmem = 232448;   // 227 KB opt-in limit per CTA on s
 constexpr int kRefThreads = 512;       // generic range kernel
 constexpr int kAuxThreads = 512;
 
+// State of the one-query fast path.  The counters live in device memory and are handed to the kernel as wins/ties/...;
+// the LAST warp to finish copies them into `host` (pinned, mapped host memory), zeroes them and the work counter for the
+// next call, and publishes `done`.
+struct SingleResult {             // in mapped host memory
+    unsigned long long wins, ties, win_types[9], passes;
+};
+struct SingleCall {               // in device memory
+    unsigned long long wins, ties, win_types[9], passes;
+    unsigned long long work_counter;
+    unsigned int ticket;
+    unsigned int abort_flag[16];
+    SingleResult* host;
+};
+
 struct EquityParams {
     DeviceTables tables;
     const uint8_t* hole;          // [Q,2] card ids
@@ -29,6 +43,9 @@ struct EquityParams {
     unsigned long long* ties;     // [Q] hero ties for best
     unsigned long long* win_types;// [Q,9] or null: hand type of the hero whenever he wins or ties
     unsigned long long* passes;   // [Q] or null: reference-mode draw attempts (montecarlo_python.py:167)
+    // ---- single blocking call (npk_equity_host with one query): no copies, no memsets ----
+    uint64_t inline_query;        // hole[2] | board[5] << 16 (bytes), used when `hole` is null
+    SingleCall* single;           // device scratch + mapped host result block, or null
     // ---- ranges (equity_ranges_kernel only) ----
     uint32_t opp_mask[6];         // 169-bit mask of the starting-hand classes an opponent may hold
     uint32_t hero_mask[6];        // the same for the hero when hero_range != 0

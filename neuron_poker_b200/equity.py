@@ -17,6 +17,7 @@ Install into the environment by assigning the attribute the env binds in its con
 """
 import ctypes
 import os
+import threading
 from collections import Counter
 
 import numpy as np
@@ -40,17 +41,39 @@ def seed(value=None):
 
 
 def _next_seed():
+    """53 random bits from the global legacy RandomState (one call; the reference's own generator)."""
     rng = _seed_state["rng"]
-    draw = rng.randint if rng is not None else np.random.randint
-    return (int(draw(0, 1 << 31)) << 31) | int(draw(0, 1 << 31))
+    return int((rng.random_sample() if rng is not None else np.random.random_sample()) * 9007199254740992.0)
+
+
+_device_cache = {}
 
 
 def _device():
-    return int(os.environ.get("NPK_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    key = (os.environ.get("NPK_DEVICE"), os.environ.get("LOCAL_RANK"))
+    d = _device_cache.get(key)
+    if d is None:
+        d = _device_cache[key] = int(key[0] if key[0] is not None else (key[1] if key[1] is not None else "0"))
+    return d
 
 
 def _u8(a):
     return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _CallBuffers(threading.local):
+    """Per-thread argument and result buffers of the one-query calls: allocated once and addressed by integer (a ctypes
+    void* parameter accepts an int), so a get_equity call creates no arrays and no ctypes objects."""
+
+    def __init__(self):
+        self.inp = np.zeros(8, dtype=np.uint8)            # hole[2] board[5] players[1]
+        self.out = np.zeros(12, dtype=np.uint64)          # wins ties types[9] passes
+        a, o = self.inp.ctypes.data, self.out.ctypes.data
+        self.p_hole, self.p_board, self.p_npl = a, a + 2, a + 7
+        self.p_wins, self.p_ties, self.p_types, self.p_passes = o, o + 8, o + 16, o + 88
+
+
+_buffers = _CallBuffers()
 
 
 def equity_counts(player_cards, table_cards, players, runs, deal_mode="uniform", seed_value=None, win_types=False,
@@ -64,21 +87,20 @@ def equity_counts(player_cards, table_cards, players, runs, deal_mode="uniform",
     if players > 10:
         raise ValueError("at most 10 players")
     hole, board = encode_query(player_cards, table_cards)
+    b = _buffers
+    b.inp[0:2] = hole
+    b.inp[2:7] = board
+    b.inp[7] = players
     L = _lib.ensure_init(_device())
-    n_players = np.array([players], dtype=np.uint8)
-    out_w = np.zeros(1, dtype=np.uint64)
-    out_t = np.zeros(1, dtype=np.uint64)
-    out_ty = np.zeros(9, dtype=np.uint64) if win_types else None
-    out_p = np.zeros(1, dtype=np.uint64) if passes else None
     s = _next_seed() if seed_value is None else int(seed_value)
-    _lib.check(L.npk_equity_host(_u8(hole), _u8(board), _u8(n_players), 1, runs, ctypes.c_uint64(s & (2**64 - 1)),
-                                 _DEAL[deal_mode], _u8(out_w), _u8(out_t), _u8(out_ty) if win_types else None,
-                                 _u8(out_p) if passes else None))
-    res = {"wins": int(out_w[0]), "ties": int(out_t[0]), "runs": runs}
+    _lib.check(L.npk_equity_host(b.p_hole, b.p_board, b.p_npl, 1, runs, s & (2**64 - 1), _DEAL[deal_mode], b.p_wins, b.p_ties,
+                                 b.p_types if win_types else None, b.p_passes if passes else None))
+    out = b.out
+    res = {"wins": int(out[0]), "ties": int(out[1]), "runs": runs}
     if win_types:
-        res["win_types"] = [int(x) for x in out_ty]
+        res["win_types"] = [int(x) for x in out[2:11]]
     if passes:
-        res["passes"] = int(out_p[0])
+        res["passes"] = int(out[11])
     return res
 
 
