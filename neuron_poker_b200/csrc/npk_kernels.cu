@@ -397,19 +397,11 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
                 attempt();
                 if (__any_sync(0xffffffffu, !ok)) {
                     uint32_t guard = 0;
+#pragma unroll 1
                     while (!ok) {
                         x = fmix32(w0 + ++guard * kGold);          // retry r draws from fmix32(word + r * golden ratio)
                         attempt();
-                        if (guard > kMaxRangeAttempts) {         // cannot happen (each attempt fails with probability 1/n)
-                            if (atomicExch(p.abort_flag, 1u) == 0u) {
-                                p.abort_flag[1] = (uint32_t)q; p.abort_flag[2] = (uint32_t)trial; p.abort_flag[3] = (uint32_t)o;
-                                p.abort_flag[4] = x; p.abort_flag[5] = n; p.abort_flag[6] = (uint32_t)avail;
-                                p.abort_flag[7] = (uint32_t)(avail >> 32); p.abort_flag[8] = id1; p.abort_flag[9] = id2;
-                                p.abort_flag[10] = i1; p.abort_flag[11] = i2; p.abort_flag[12] = c1; p.abort_flag[13] = c2;
-                                p.abort_flag[14] = t1; p.abort_flag[15] = t2;
-                            }
-                            break;
-                        }
+                        if (guard > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); break; }   // cannot happen: an attempt fails with probability 1/n
                     }
                 }
                 slot[2 * o] = fy_addr + i1 * 128u; slot[2 * o + 1] = fy_addr + i2 * 128u;
@@ -418,42 +410,39 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
                 sts_u32(slot[2 * o + 1], i1 == n - 2u ? t1 : t2);
                 avail &= ~((1ull << id1) | (1ull << id2));
             }
+            // The highest unseen card never reaches the board (:188) -- and since it is never dealt there, it stays the
+            // highest for all NB board draws: find it once and compare the low six descriptor bits (suit, 12 - rank).
+            uint32_t top6 = 0xFFFFFFFFu;
+            if (NB > 0) {
+                const uint32_t top = 63u - (uint32_t)__clzll((long long)avail);
+                top6 = ((top & 3u) << 4) | (12u - (top >> 2));
+            }
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 constexpr uint32_t kGold = 0x9E3779B9u;
                 const uint32_t n = (uint32_t)(N - 2 * NOPP - b);
                 const uint32_t t1 = lds_u32(fy_addr + (n - 1u) * 128u);
-                const uint32_t top = 63u - (uint32_t)__clzll((long long)avail);       // never dealt to the board (:188)
                 const uint32_t w0 = w[NOPP + b];
-                uint32_t x = w0, i1, c1, id1;
+                uint32_t x = w0, i1, c1;
                 bool ok;
                 auto attempt = [&]() {
                     i1 = __umulhi(x, n);
                     c1 = lds_u32(fy_addr + i1 * 128u);
-                    id1 = desc_card(c1);
-                    ok = id1 != top;
+                    ok = (c1 & 63u) != top6;
                 };
                 attempt();
                 if (__any_sync(0xffffffffu, !ok)) {
                     uint32_t guard = 0;
+#pragma unroll 1
                     while (!ok) {
-                        x = fmix32(w0 + ++guard * kGold);          // retry r draws from fmix32(word + r * golden ratio)
+                        x = fmix32(w0 + ++guard * kGold);
                         attempt();
-                        if (guard > kMaxRangeAttempts) {
-                            if (atomicExch(p.abort_flag, 1u) == 0u) {
-                                p.abort_flag[1] = (uint32_t)q; p.abort_flag[2] = (uint32_t)trial; p.abort_flag[3] = 100u + (uint32_t)b;
-                                p.abort_flag[4] = x; p.abort_flag[5] = n; p.abort_flag[6] = (uint32_t)avail;
-                                p.abort_flag[7] = (uint32_t)(avail >> 32); p.abort_flag[8] = id1; p.abort_flag[9] = top;
-                                p.abort_flag[10] = i1; p.abort_flag[12] = c1; p.abort_flag[14] = t1;
-                            }
-                            break;
-                        }
+                        if (guard > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); break; }
                     }
                 }
                 slot[2 * NOPP + b] = fy_addr + i1 * 128u;
                 dv[2 * NOPP + b] = c1;
                 sts_u32(slot[2 * NOPP + b], t1);
-                avail &= ~(1ull << id1);
             }
 #pragma unroll
             for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[k]);

@@ -379,3 +379,26 @@ def test_invalid_queries_are_reported(torch_mod):
         _run_batch(torch, [[0, 1]], [pad_board([])], [11], 10, 0, "reference")
     out = _run_batch(torch, np.zeros((0, 2)), np.zeros((0, 5)), np.zeros((0,)), 10, 0, "uniform")
     assert out["wins"].shape == (0,)
+
+
+def test_one_query_fast_path_equals_the_batched_path(torch_mod):
+    """npk_equity_host with one query takes a copy-free path (query in the kernel parameters, counters resident on the
+    device and reset by the last warp, results in mapped host memory).  Same seed, same query => the same counters as
+    the batched path, call after call, in both dealing modes and with win types / passes."""
+    import neuron_poker_b200 as npk
+    spots = [(["AS", "KS"], ["2C", "7D", "KH"], 6, 10000), (["3H", "3S"], ["8S", "4S", "QH", "8C", "4H"], 2, 777),
+             (["7D", "7C"], [], 10, 4097), (["AS", "AD"], [], 1, 100), (["JD", "JS"], ["8C", "TC", "JC", "5H"], 3, 31)]
+    for rep in range(3):
+        for mode in ("uniform", "reference"):
+            for h, b, p, runs in spots:
+                one = npk.equity_counts(h, b, p, runs, deal_mode=mode, seed_value=99 + rep, win_types=True,
+                                        passes=(mode == "reference"))
+                two = npk.equity_counts_batch(np.array([ids(h), ids(h)], dtype=np.uint8),
+                                              np.array([pad_board(ids(b))] * 2, dtype=np.uint8),
+                                              np.array([p, p], dtype=np.uint8), runs, seed_value=99 + rep, deal_mode=mode,
+                                              win_types=True, passes=(mode == "reference"))
+                assert (one["wins"], one["ties"]) == (int(two["wins"][0]), int(two["ties"][0])), (mode, h, b, p)
+                assert one["win_types"] == [int(x) for x in two["win_types"][0]]
+                if mode == "reference":
+                    assert one["passes"] == int(two["passes"][0])
+                assert one["wins"] + one["ties"] <= runs
