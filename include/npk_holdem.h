@@ -51,6 +51,8 @@ typedef struct NpkHoldemTable {
     double reward;                      /* reward of the last npk_holdem_step (env.py:280-306; -1 for an illegal move) */
     double small_blind, big_blind, initial_stacks;
     uint64_t rng_counter;               /* cards drawn since init: draw k uses Philox word k of this table's stream */
+    uint64_t deck_mask;                 /* remaining deck: bit c set <=> card c still in it.  The reference's deck is an
+                                           ordered list that only ever loses elements, so deck.pop(j) is "the j-th set bit" */
     /* PlayerCycle (cycle.py:13-37) */
     int32_t idx, dealer_idx, step_counter, cycle_round_number, max_steps_total /* 0 = None */, last_raiser_step,
         max_steps_after_raiser, max_steps_after_big_blind, last_raiser /* -1 = None */, checkers,
@@ -69,8 +71,7 @@ typedef struct NpkHoldemTable {
     uint8_t num_raises[NPK_MAX_SEATS][4];
     uint8_t cards[NPK_MAX_SEATS][2];    /* 0xFF = no card */
     uint8_t table_cards[5];
-    uint8_t deck[52];                   /* remaining deck, ordered like the reference's list */
-    uint8_t reserved[5];
+    uint8_t reserved[1];
 } NpkHoldemTable;
 
 int64_t npk_holdem_table_bytes(void);

@@ -31,14 +31,31 @@ __device__ __forceinline__ uint32_t deal_word(const HoldemCtx& c, uint64_t k)
     return w[k & 3];
 }
 
+// k-th (0-based) set bit of a 52-bit mask, by halving on popcounts
+__device__ __forceinline__ int nth_set_bit(uint64_t m, int k)
+{
+    uint32_t w = (uint32_t)m;
+    int base = 0;
+    const int c = __popc(w);
+    if (k >= c) { k -= c; w = (uint32_t)(m >> 32); base = 32; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const uint32_t low = (1u << s) - 1u;
+        const int cl = __popc(w & low);
+        if (k >= cl) { k -= cl; w >>= s; base += s; } else { w &= low; }
+    }
+    return base;
+}
+
+// deck.pop(np.random.randint(0, len(deck))) (env.py:680, 686) on the ordered deck = remove the j-th remaining card
 __device__ uint8_t pop_random_card(T& t, const HoldemCtx& c)
 {
     const uint32_t n = (uint32_t)t.n_deck;
     const uint32_t j = __umulhi(deal_word(c, t.rng_counter++), n);
-    const uint8_t card = t.deck[j];
-    for (uint32_t i = j; i + 1 < n; i++) t.deck[i] = t.deck[i + 1];       // list.pop(j)
+    const int card = nth_set_bit(t.deck_mask, (int)j);
+    t.deck_mask &= ~(1ull << card);
     t.n_deck = (int32_t)n - 1;
-    return card;
+    return (uint8_t)card;
 }
 
 // hand value through the lookup tables in global memory (tools/hand_evaluator.py:27-119 ordering)
@@ -329,7 +346,7 @@ __device__ void start_new_hand(T& t, const HoldemCtx& c)                 // env.
     if (check_game_over(t)) return;
     t.n_table_cards = 0;
     for (int i = 0; i < 5; i++) t.table_cards[i] = 0xFF;
-    for (int i = 0; i < 52; i++) t.deck[i] = (uint8_t)i;                 // _create_card_deck: id = 4*rank + suit
+    t.deck_mask = (1ull << 52) - 1ull;                                   // _create_card_deck: id = 4*rank + suit
     t.n_deck = 52;
     t.stage = NPK_PREFLOP;
     t.community_pot = 0;
@@ -416,17 +433,16 @@ __global__ void holdem_reset_done_kernel(T* tables, long long n, HoldemCtx c0)
 }
 
 // HoldemTable.step for a player that is not an autoplay agent (env.py:170-200)
-__global__ void holdem_step_kernel(T* tables, long long n, const int8_t* __restrict__ actions, double* __restrict__ rewards,
-                                   HoldemCtx c0, int restart_finished)
+// The tables of a block are staged in shared memory (coalesced 8-byte copies in and out): the state machine is a long
+// chain of dependent small accesses in 32 different control-flow paths per warp, which is slow against L2 and cheap
+// against shared memory; HBM sees each table exactly once in each direction.
+constexpr int kStepThreads = 64;                                         // 64 x 760 B = 48,640 B of shared memory
+static_assert(sizeof(T) % 8 == 0, "NpkHoldemTable is copied in 8-byte units");
+static_assert(kStepThreads * sizeof(T) <= 48 * 1024, "the staged tables must fit the default shared-memory limit");
+
+__device__ void step_one_table(T& t, int action, const HoldemCtx& c, int restart_finished, double* reward_out)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int action = actions[i];
-    if (action < 0) return;
-    T& t = tables[i];                       // in place (760 B per table; a step touches a fraction of it)
-    if (t.done || t.error) { if (rewards) rewards[i] = 0; return; }
-    HoldemCtx c = c0;
-    c.table_id = c0.table_id + (uint32_t)i;
+    if (t.done || t.error) { if (reward_out) *reward_out = 0; return; }
     t.reward = 0;
     t.acting_agent = t.idx;
     const uint32_t legal = legal_moves(t);
@@ -451,8 +467,40 @@ __global__ void holdem_step_kernel(T* tables, long long n, const int8_t* __restr
             }
         }
     }
-    if (rewards) rewards[i] = t.reward;
+    if (reward_out) *reward_out = t.reward;
     if (restart_finished && t.done) { t.error = 0; table_reset(t, c); }   // a new env.reset() for a finished game
+}
+
+// HoldemTable.step for a player that is not an autoplay agent (env.py:170-200)
+__global__ void __launch_bounds__(kStepThreads) holdem_step_kernel(T* tables, long long n, const int8_t* __restrict__ actions,
+                                                                   double* __restrict__ rewards, HoldemCtx c0,
+                                                                   int restart_finished)
+{
+    extern __shared__ __align__(16) unsigned long long s_words[];
+    T* s_tab = reinterpret_cast<T*>(s_words);
+    const long long first = (long long)blockIdx.x * kStepThreads;
+    const long long count = min((long long)kStepThreads, n - first);
+    if (count <= 0) return;
+    constexpr int kWordsPerTable = (int)(sizeof(T) / 8);
+    const unsigned long long* g_words = reinterpret_cast<const unsigned long long*>(tables + first);
+    const int total_words = (int)count * kWordsPerTable;
+    for (int w = threadIdx.x; w < total_words; w += kStepThreads) s_words[w] = g_words[w];
+    __syncthreads();
+    const long long i = first + threadIdx.x;
+    bool touched = false;
+    if (threadIdx.x < count) {
+        const int action = actions[i];
+        if (action >= 0) {
+            HoldemCtx c = c0;
+            c.table_id = c0.table_id + (uint32_t)i;
+            step_one_table(s_tab[threadIdx.x], action, c, restart_finished, rewards ? rewards + i : nullptr);
+            touched = true;
+        }
+    }
+    // write back only if some table of the block was stepped
+    if (!__syncthreads_or(touched)) return;
+    unsigned long long* o_words = reinterpret_cast<unsigned long long*>(tables + first);
+    for (int w = threadIdx.x; w < total_words; w += kStepThreads) o_words[w] = s_words[w];
 }
 
 __global__ void holdem_queries_kernel(const T* __restrict__ tables, long long n, uint8_t* __restrict__ hole,
@@ -547,8 +595,9 @@ cudaError_t launch_holdem_reset_done(const DeviceTables& tab, void* tables, long
 cudaError_t launch_holdem_step(const DeviceTables& tab, void* tables, long long n, const int8_t* actions, double* rewards,
                                uint64_t seed, long long table_offset, int restart_finished, cudaStream_t s)
 {
-    holdem_step_kernel<<<blocks_for(n), kHoldemThreads, 0, s>>>(static_cast<T*>(tables), n, actions, rewards,
-                                                               make_ctx(tab, seed, table_offset), restart_finished);
+    const int blocks = (int)((n + kStepThreads - 1) / kStepThreads);
+    holdem_step_kernel<<<blocks, kStepThreads, kStepThreads * sizeof(T), s>>>(static_cast<T*>(tables), n, actions, rewards,
+                                                                             make_ctx(tab, seed, table_offset), restart_finished);
     return cudaGetLastError();
 }
 

@@ -50,7 +50,7 @@ TABLE_DTYPE = np.dtype([
     ("stack", "f8", (_S,)), ("player_pots", "f8", (_S,)), ("player_max_win", "f8", (_S,)), ("funds_prev", "f8", (_S,)),
     ("funds_last", "f8", (_S,)), ("community_pot", "f8"), ("current_round_pot", "f8"), ("min_call", "f8"),
     ("last_player_pot", "f8"), ("reward", "f8"), ("small_blind", "f8"), ("big_blind", "f8"), ("initial_stacks", "f8"),
-    ("rng_counter", "u8"),
+    ("rng_counter", "u8"), ("deck_mask", "u8"),
     ("idx", "i4"), ("dealer_idx", "i4"), ("step_counter", "i4"), ("cycle_round_number", "i4"), ("max_steps_total", "i4"),
     ("last_raiser_step", "i4"), ("max_steps_after_raiser", "i4"), ("max_steps_after_big_blind", "i4"), ("last_raiser", "i4"),
     ("checkers", "i4"), ("max_remaining_steps_without_raising", "i4"),
@@ -59,7 +59,7 @@ TABLE_DTYPE = np.dtype([
     ("hands_played", "i4"), ("error", "i4"), ("legal_moves", "u4"),
     ("can_still", "u1", (_S,)), ("out_of_cash", "u1", (_S,)), ("folder", "u1", (_S,)), ("alive", "u1", (_S,)),
     ("first_action", "u1", (_S,)), ("autoplay", "u1", (_S,)), ("num_raises", "u1", (_S, 4)), ("cards", "u1", (_S, 2)),
-    ("table_cards", "u1", (5,)), ("deck", "u1", (52,)), ("reserved", "u1", (5,)),
+    ("table_cards", "u1", (5,)), ("reserved", "u1", (1,)),
 ], align=True)
 
 
