@@ -77,3 +77,52 @@ def test_shard_arithmetic():
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= 1
             assert sum(c for _, c in (npk_dist.trial_shard(n, r, world) for r in range(world))) == n
+
+
+# ---- the same algebra on real GPUs over NCCL (skipped on boxes with fewer than two GPUs) -------------------------------
+def _nccl_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["NPK_DEVICE"] = str(rank)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rng = np.random.default_rng(1)
+    Q = 37
+    cards = np.stack([rng.permutation(52)[:5] for _ in range(Q)]).astype(np.uint8)
+    hole = torch.as_tensor(cards[:, :2].copy()).cuda()
+    board = torch.full((Q, 5), 255, dtype=torch.uint8)
+    board[:, :3] = torch.as_tensor(cards[:, 2:5].copy())
+    board = board.cuda()
+    npl = torch.full((Q,), 6, dtype=torch.uint8).cuda()
+    out = {}
+    for mode in ("uniform", "reference"):
+        for by in ("query", "trial"):
+            w, t = npk_dist.sharded_equity(hole, board, npl, 5001, seed_value=SEED, deal_mode=mode, by=by, uniform_shape=(6, 3))
+            out[(mode, by)] = (w.cpu().tolist(), t.cpu().tolist())
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_sharded_counts_equal_unsharded():
+    """Two ranks, two GPUs: query blocks (all-gather) and trial ranges (all-reduce of the counters) both reproduce the
+    single-GPU counts bit for bit, in both dealing modes (5,001 trials: an odd split, so trial pairs straddle ranks)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import neuron_poker_b200 as npk
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    rng = np.random.default_rng(1)
+    Q = 37
+    cards = np.stack([rng.permutation(52)[:5] for _ in range(Q)]).astype(np.uint8)
+    board = np.full((Q, 5), 255, dtype=np.uint8)
+    board[:, :3] = cards[:, 2:5]
+    for mode in ("uniform", "reference"):
+        one = npk.get_equity_batch(cards[:, :2].copy(), board, np.full(Q, 6, dtype=np.uint8), 5001, seed_value=SEED,
+                                   deal_mode=mode, uniform_shape=(6, 3))
+        want = (one["wins"].cpu().tolist(), one["ties"].cpu().tolist())
+        for r in range(world):
+            for by in ("query", "trial"):
+                assert ret[r][(mode, by)] == want, (mode, by, r)
