@@ -14,8 +14,10 @@
  *   npk_holdem_queries   the get_equity call of _get_environment                      gym_env/env.py:249-264
  *   npk_holdem_decide    agents/agent_consider_equity.py:21-58 and agents/agent_random.py:19-29
  *
- * Not mirrored (outside the hot path): the observation vector / StageData bookkeeping (env.py:21-63, 383-391),
- * rendering, the pandas funds history beyond the two rows the reward reads, logging.
+ *   npk_holdem_observe   the observation vector `array_everything` of _get_environment     gym_env/env.py:232-270
+ *                        (PlayerData, CommunityData, StageData: env.py:24-63; StageData updates :383-391)
+ *
+ * Not mirrored (outside the hot path): rendering, the pandas funds history beyond the two rows the reward reads, logging.
  *
  * State is an array of NpkHoldemTable structs in DEVICE memory owned by the caller (a torch tensor of
  * npk_holdem_table_bytes() * N bytes); a host copy of it is a plain C struct array (numpy structured dtype in
@@ -51,6 +53,7 @@ typedef struct NpkHoldemTable {
     double reward;                      /* reward of the last npk_holdem_step (env.py:280-306; -1 for an illegal move) */
     double small_blind, big_blind, initial_stacks;
     uint64_t rng_counter;               /* cards drawn since init: draw k uses Philox word k of this table's stream */
+    double* stage_data;                 /* this table's [4][6][NPK_MAX_SEATS] StageData block, or NULL (npk_holdem_attach_stage_data) */
     uint64_t deck_mask;                 /* remaining deck: bit c set <=> card c still in it.  The reference's deck is an
                                            ordered list that only ever loses elements, so deck.pop(j) is "the j-th set bit" */
     /* PlayerCycle (cycle.py:13-37) */
@@ -90,6 +93,25 @@ int npk_holdem_init(void* tables, int64_t N, int n_players, double initial_stack
  * reward has been recorded. */
 int npk_holdem_step(void* tables, int64_t N, const int8_t* actions, double* rewards, uint64_t seed, int64_t table_offset,
                     int restart_finished, void* stream);
+
+/* StageData bookkeeping for the observation vector (optional; the equity agents do not read it).  stage_data is a device
+ * array [N][4 streets][6 fields][NPK_MAX_SEATS] of double, fields in the order of StageData (env.py:40-50): calls,
+ * raises, min_call_at_action, contribution, stack_at_action, community_pot_at_action.  Attach it right after
+ * npk_holdem_init (it is cleared, and the blinds already posted are recorded): npk_holdem_step then keeps it up to
+ * date (cleared when a hand starts, written by _process_decision, env.py:383-391).  Pass NULL to detach. */
+#define NPK_STAGE_DATA_DOUBLES (4 * 6 * NPK_MAX_SEATS)
+int npk_holdem_attach_stage_data(void* tables, int64_t N, double* stage_data, void* stream);
+
+/* Observation length for n_players seats: 22 + 51 * n_players (328 for six players). */
+int64_t npk_holdem_observation_size(int n_players);
+/* array_everything (env.py:266-270) for every table: obs [N, 22 + 51*n] double =
+ *   PlayerData   position, equity_to_river_alive, equity_to_river_2plr (nan), equity_to_river_3plr (nan), stack[n]
+ *   CommunityData current_player_position[n] (never set by the reference: zeros), stage one-hot[4], community_pot,
+ *                current_round_pot, active_players[n] (zeros), big_blind, small_blind, legal_moves[10]
+ *   StageData x 8 calls[n] raises[n] min_call_at_action[n] contribution[n] stack_at_action[n] community_pot_at_action[n]
+ *                (the reference only ever writes entries 0..3: its round_number_in_street stays 0, env.py:382)
+ * money divided by big_blind * 100 like the reference.  equity [N] double or NULL (then nan).  Needs attached stage data. */
+int npk_holdem_observe(const void* tables, int64_t N, const double* equity, double* obs, void* stream);
 
 /* The get_equity arguments of _get_environment for every table: hole [N,2] = cards of the current player (of the
  * winner once the game is over), board [N,5] with 0xFF padding, n_players [N] = sum(player_cycle.alive).

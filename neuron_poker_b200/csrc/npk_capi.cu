@@ -805,6 +805,30 @@ int npk_holdem_step(void* tables, int64_t N, const int8_t* actions, double* rewa
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_step_kernel launch");
 }
 
+int npk_holdem_attach_stage_data(void* tables, int64_t N, double* stage_data, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaError_t e = npk::launch_holdem_attach(tables, N, stage_data, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_attach_kernel launch");
+}
+
+int64_t npk_holdem_observation_size(int n_players) { return 22 + 51 * (int64_t)n_players; }
+
+int npk_holdem_observe(const void* tables, int64_t N, const double* equity, double* obs, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!tables || !obs) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    cudaError_t e = npk::launch_holdem_observe(tables, N, equity, obs, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "holdem_observe_kernel launch");
+}
+
 int npk_holdem_queries(const void* tables, int64_t N, uint8_t* hole, uint8_t* board, uint8_t* n_players, uint8_t* active,
                        void* stream)
 {

@@ -213,6 +213,17 @@ __device__ void process_decision(T& t, int action)
         }
         t.min_call = fmax(t.min_call, contribution);
         t.player_max_win[seat] += contribution;
+        if (t.stage_data && t.stage >= 0 && t.stage <= 3) {              // StageData, env.py:381-391
+            double* sd = t.stage_data + t.stage * 6 * NPK_MAX_SEATS;     // rnd = stage.value + 0 (env.py:382)
+            const int pos = t.idx;
+            const double unit = t.big_blind * 100;
+            sd[0 * NPK_MAX_SEATS + pos] = action == NPK_CALL ? 1.0 : 0.0;
+            sd[1 * NPK_MAX_SEATS + pos] = (action == NPK_RAISE_2POT || action == NPK_RAISE_HALF_POT || action == NPK_RAISE_POT) ? 1.0 : 0.0;
+            sd[2 * NPK_MAX_SEATS + pos] = t.min_call / unit;
+            sd[3 * NPK_MAX_SEATS + pos] += contribution / unit;
+            sd[4 * NPK_MAX_SEATS + pos] = t.stack[seat] / unit;
+            sd[5 * NPK_MAX_SEATS + pos] = t.community_pot / unit;
+        }
     }
     update_alive(t);
 }
@@ -344,6 +355,8 @@ __device__ void start_new_hand(T& t, const HoldemCtx& c)                 // env.
     for (int i = 0; i < t.n_players; i++)
         for (int s = 0; s < 4; s++) t.num_raises[i][s] = 0;
     if (check_game_over(t)) return;
+    if (t.stage_data)                                                    // fresh StageData objects (env.py:405)
+        for (int k = 0; k < NPK_STAGE_DATA_DOUBLES; k++) t.stage_data[k] = 0.0;
     t.n_table_cards = 0;
     for (int i = 0; i < 5; i++) t.table_cards[i] = 0xFF;
     t.deck_mask = (1ull << 52) - 1ull;                                   // _create_card_deck: id = 4*rank + suit
@@ -503,6 +516,66 @@ __global__ void __launch_bounds__(kStepThreads) holdem_step_kernel(T* tables, lo
     for (int w = threadIdx.x; w < total_words; w += kStepThreads) o_words[w] = s_words[w];
 }
 
+// Attach the StageData array.  The first hand has already been dealt by init, so the blinds it posted are replayed into
+// the fresh block: small blind = seat after the dealer, big blind the one after (only the players who were dealt in).
+__global__ void holdem_attach_kernel(T* tables, long long n, double* stage_data)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T& t = tables[i];
+    t.stage_data = stage_data ? stage_data + i * NPK_STAGE_DATA_DOUBLES : nullptr;
+    if (!stage_data) return;
+    double* sd = t.stage_data;
+    for (int k = 0; k < NPK_STAGE_DATA_DOUBLES; k++) sd[k] = 0.0;
+    if (t.done || t.stage != NPK_PREFLOP || t.hands_played != 0 || t.funds_rows != 1) return;
+    // Freshly reset table: exactly two _process_decision calls (the blinds) have happened.  The reference recorded,
+    // for each of them, the values right after the contribution (env.py:383-391).
+    const double unit = t.big_blind * 100;
+    int seat = t.dealer_idx;
+    double running_min_call = 0;
+    for (int b = 0; b < 2; b++) {
+        do { seat = (seat + 1) % t.n_players; } while (t.player_pots[seat] == 0 && t.stack[seat] == t.initial_stacks);
+        const double c = t.player_pots[seat];
+        running_min_call = fmax(running_min_call, c);
+        sd[2 * NPK_MAX_SEATS + seat] = running_min_call / unit;
+        sd[3 * NPK_MAX_SEATS + seat] = c / unit;
+        sd[4 * NPK_MAX_SEATS + seat] = t.stack[seat] / unit;
+        sd[5 * NPK_MAX_SEATS + seat] = 0.0;
+    }
+}
+
+// array_everything (env.py:232-270)
+__global__ void holdem_observe_kernel(const T* __restrict__ tables, long long n, const double* __restrict__ equity,
+                                      double* __restrict__ obs)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const T& t = tables[i];
+    const int np = t.n_players;
+    const int width = 22 + 51 * np;
+    double* o = obs + i * width;
+    const double unit = t.big_blind * 100;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    int k = 0;
+    o[k++] = (double)t.current_player;                                   // PlayerData.position = current_player.seat
+    o[k++] = equity ? equity[i] : nan;
+    o[k++] = nan; o[k++] = nan;                                          // calculate_equity=False (env.py:256-259)
+    for (int s = 0; s < np; s++) o[k++] = t.stack[s] / unit;
+    for (int s = 0; s < np; s++) o[k++] = 0.0;                           // current_player_position: never set
+    const int st = t.stage < 3 ? t.stage : 3;
+    for (int s = 0; s < 4; s++) o[k++] = s == st ? 1.0 : 0.0;
+    o[k++] = t.community_pot / unit;
+    o[k++] = t.current_round_pot / unit;
+    for (int s = 0; s < np; s++) o[k++] = 0.0;                           // active_players: never set
+    o[k++] = t.big_blind;
+    o[k++] = t.small_blind;
+    for (int a = 0; a < 10; a++) o[k++] = (t.legal_moves >> a & 1u) ? 1.0 : 0.0;
+    for (int r = 0; r < 8; r++)
+        for (int f = 0; f < 6; f++)
+            for (int s = 0; s < np; s++)
+                o[k++] = (r < 4 && t.stage_data) ? t.stage_data[(r * 6 + f) * NPK_MAX_SEATS + s] : 0.0;
+}
+
 __global__ void holdem_queries_kernel(const T* __restrict__ tables, long long n, uint8_t* __restrict__ hole,
                                       uint8_t* __restrict__ board, uint8_t* __restrict__ n_players, uint8_t* __restrict__ active)
 {
@@ -598,6 +671,18 @@ cudaError_t launch_holdem_step(const DeviceTables& tab, void* tables, long long 
     const int blocks = (int)((n + kStepThreads - 1) / kStepThreads);
     holdem_step_kernel<<<blocks, kStepThreads, kStepThreads * sizeof(T), s>>>(static_cast<T*>(tables), n, actions, rewards,
                                                                              make_ctx(tab, seed, table_offset), restart_finished);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_holdem_attach(void* tables, long long n, double* stage_data, cudaStream_t s)
+{
+    holdem_attach_kernel<<<blocks_for(n), kHoldemThreads, 0, s>>>(static_cast<T*>(tables), n, stage_data);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_holdem_observe(const void* tables, long long n, const double* equity, double* obs, cudaStream_t s)
+{
+    holdem_observe_kernel<<<blocks_for(n), kHoldemThreads, 0, s>>>(static_cast<const T*>(tables), n, equity, obs);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,8 @@ cudaError_t launch_holdem_reset_done(const DeviceTables& tab, void* tables, long
                                      cudaStream_t s);
 cudaError_t launch_holdem_step(const DeviceTables& tab, void* tables, long long n, const int8_t* actions, double* rewards,
                                uint64_t seed, long long table_offset, int restart_finished, cudaStream_t s);
+cudaError_t launch_holdem_attach(void* tables, long long n, double* stage_data, cudaStream_t s);
+cudaError_t launch_holdem_observe(const void* tables, long long n, const double* equity, double* obs, cudaStream_t s);
 cudaError_t launch_holdem_queries(const void* tables, long long n, uint8_t* hole, uint8_t* board, uint8_t* n_players,
                                   uint8_t* active, cudaStream_t s);
 cudaError_t launch_holdem_decide(const DeviceTables& tab, const void* tables, long long n, const uint64_t* wins,

@@ -50,7 +50,7 @@ TABLE_DTYPE = np.dtype([
     ("stack", "f8", (_S,)), ("player_pots", "f8", (_S,)), ("player_max_win", "f8", (_S,)), ("funds_prev", "f8", (_S,)),
     ("funds_last", "f8", (_S,)), ("community_pot", "f8"), ("current_round_pot", "f8"), ("min_call", "f8"),
     ("last_player_pot", "f8"), ("reward", "f8"), ("small_blind", "f8"), ("big_blind", "f8"), ("initial_stacks", "f8"),
-    ("rng_counter", "u8"), ("deck_mask", "u8"),
+    ("rng_counter", "u8"), ("stage_data", "u8"), ("deck_mask", "u8"),
     ("idx", "i4"), ("dealer_idx", "i4"), ("step_counter", "i4"), ("cycle_round_number", "i4"), ("max_steps_total", "i4"),
     ("last_raiser_step", "i4"), ("max_steps_after_raiser", "i4"), ("max_steps_after_big_blind", "i4"), ("last_raiser", "i4"),
     ("checkers", "i4"), ("max_remaining_steps_without_raising", "i4"),
@@ -73,6 +73,10 @@ def _bind(L):
     L.npk_holdem_step.argtypes = [vp, i64, vp, vp, u64, i64, i32, vp]
     L.npk_holdem_queries.argtypes = [vp, i64, vp, vp, vp, vp, vp]
     L.npk_holdem_decide.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, vp, u64, i64, i64, vp, vp]
+    L.npk_holdem_attach_stage_data.argtypes = [vp, i64, vp, vp]
+    L.npk_holdem_observation_size.argtypes = [i32]
+    L.npk_holdem_observation_size.restype = i64
+    L.npk_holdem_observe.argtypes = [vp, i64, vp, vp, vp]
     if L.npk_holdem_table_bytes() != TABLE_DTYPE.itemsize:
         raise RuntimeError("NpkHoldemTable is %d bytes in libnpk.so but %d in holdem.TABLE_DTYPE"
                            % (L.npk_holdem_table_bytes(), TABLE_DTYPE.itemsize))
@@ -130,6 +134,7 @@ class HoldemTables(object):
         self.rewards = torch.zeros(self.n_tables, dtype=torch.float64, device=self.device)
         self.decisions = 0
         self._q = None
+        self.stage_data = None
         self.reset()
 
     # ---- plumbing ----
@@ -216,6 +221,31 @@ class HoldemTables(object):
         actions = self.decide(agents, wins=out["wins"], ties=out["ties"], runs=runs)
         self.step(actions, restart_finished=restart_finished)
         return actions
+
+    # ---- observations ----
+    def enable_observations(self):
+        """Attach StageData bookkeeping (env.py:40-50, 383-391) so that observe() can build the reference's observation
+        vector.  Call right after construction / reset()."""
+        torch = self.torch
+        self.stage_data = torch.zeros((self.n_tables, 4, 6, MAX_SEATS), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_attach_stage_data(self.buf.data_ptr(), self.n_tables, self.stage_data.data_ptr(),
+                                                           self._stream()))
+        return self
+
+    def observe(self, equity=None):
+        """`array_everything` of _get_environment (env.py:266-270) for every table: float64 CUDA tensor
+        [N, 22 + 51 * n_players].  equity: [N] float64 CUDA tensor for equity_to_river_alive, or None (nan)."""
+        torch = self.torch
+        if getattr(self, "stage_data", None) is None:
+            raise RuntimeError("call enable_observations() first")
+        width = int(self.L.npk_holdem_observation_size(self.n_players))
+        obs = torch.empty((self.n_tables, width), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.npk_holdem_observe(self.buf.data_ptr(), self.n_tables,
+                                                 equity.data_ptr() if equity is not None else None, obs.data_ptr(),
+                                                 self._stream()))
+        return obs
 
     # ---- host views ----
     def state(self):

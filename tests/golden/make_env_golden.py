@@ -16,7 +16,8 @@ How the reference is driven:
 
 Files written:
   env_traces.npz     per game: its configuration, the action sequence and the table state after reset and after
-                     every step (stage, seats, stacks, pots, cards, legal moves, cycle counters, reward, done)
+                     every step (stage, seats, stacks, pots, cards, legal moves, cycle counters, reward, done, and the
+                     observation vector array_everything with the stub equity 0.5)
   agent_cases.json   agents/agent_consider_equity.py::Player.action on random (equity, legal moves, thresholds)
 """
 import contextlib
@@ -124,7 +125,8 @@ def snapshot(env, dealer, reward):
                -1 if cyc.last_raiser is None else cyc.last_raiser, cyc.checkers, cyc.max_steps_total or 0,
                len(env.deck or []), dealer.k, cyc.dealer_idx]
     money = [env.community_pot, env.current_round_pot, env.min_call, float(reward)]
-    return np.array(scalars, dtype=np.int64), np.array(money, dtype=np.float64), seat, cards, tc
+    obs = np.asarray(env.array_everything, dtype=np.float64)           # the observation vector (env.py:266-270)
+    return np.array(scalars, dtype=np.int64), np.array(money, dtype=np.float64), seat, cards, tc, obs
 
 
 def play(game, n_players, stacks, sb, bb, max_raises, max_steps, illegal_rate):
@@ -172,7 +174,7 @@ def build_traces():
             actions, snaps = play(game, n_players, stacks, sb, bb, max_raises, max_steps=400,
                                   illegal_rate=0.08 if game % 2 else 0.0)
             out["g%d_actions" % game] = np.array(actions, dtype=np.int8)
-            for name, j in (("scalars", 0), ("money", 1), ("seat", 2), ("cards", 3), ("table_cards", 4)):
+            for name, j in (("scalars", 0), ("money", 1), ("seat", 2), ("cards", 3), ("table_cards", 4), ("obs", 5)):
                 out["g%d_%s" % (game, name)] = np.stack([s[j] for s in snaps])
             meta.append({"game": game, "config": ci, "n_players": n_players, "initial_stacks": stacks, "small_blind": sb,
                          "big_blind": bb, "max_raises": max_raises, "steps": len(actions),

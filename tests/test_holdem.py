@@ -56,9 +56,25 @@ def _compare(game, step, st, z, meta, n):
     assert (st["table_cards"] == z["g%d_table_cards" % game][step]).all(), (where, "table_cards")
 
 
+def _compare_obs(game, step, got, z, n, done):
+    """The observation vector array_everything (env.py:266-270), bit for bit (nan == nan).  Once the game is over the
+    reference's legal-move flags are the stale ones of the finished step (env.py:233-234 skips the refresh): skipped."""
+    want = z["g%d_obs" % game][step]
+    assert got.shape == want.shape == (22 + 51 * n,)
+    keep = np.ones(len(want), dtype=bool)
+    if done:
+        lm = 4 + n + n + 4 + 2 + n + 2
+        keep[lm:lm + 10] = False
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    assert same[keep].all(), ("game %d step %d" % (game, step), np.nonzero(~same & keep)[0][:8], got[~same & keep][:8],
+                              want[~same & keep][:8])
+
+
 @pytest.mark.gpu
 def test_tables_replay_the_reference_traces(cuda_device, traces):
-    """Every game of env_traces.npz, all games of one configuration stepped together as one batch."""
+    """Every game of env_traces.npz, all games of one configuration stepped together as one batch: the table state and
+    the observation vector after reset and after every step."""
+    import torch
     from neuron_poker_b200.holdem import HoldemTables
     z, meta = traces
     seed = int(z["seed"][0])
@@ -71,17 +87,23 @@ def test_tables_replay_the_reference_traces(cuda_device, traces):
         tb = HoldemTables(len(group), n_players=g0["n_players"], initial_stacks=g0["initial_stacks"],
                           small_blind=g0["small_blind"], big_blind=g0["big_blind"],
                           max_raises_per_player_round=g0["max_raises"], seed=seed, table_offset=g0["game"])
+        tb.enable_observations()
+        half = torch.full((len(group),), 0.5, dtype=torch.float64, device=tb.device)     # the traces' stub equity
         st = tb.state()
+        obs = tb.observe(half).cpu().numpy()
         for i, g in enumerate(group):
             _compare(g["game"], 0, st[i], z, meta, g["n_players"])
+            _compare_obs(g["game"], 0, obs[i], z, g["n_players"], False)
         for step in range(max(g["steps"] for g in group)):
             acts = np.array([z["g%d_actions" % g["game"]][step] if step < g["steps"] else -1 for g in group], dtype=np.int8)
             tb.step(acts)
             st = tb.state()
+            obs = tb.observe(half).cpu().numpy()
             for i, g in enumerate(group):
                 if step < g["steps"]:
                     assert st[i]["error"] == 0
                     _compare(g["game"], step + 1, st[i], z, meta, g["n_players"])
+                    _compare_obs(g["game"], step + 1, obs[i], z, g["n_players"], bool(st[i]["done"]))
                     total += 1
     assert total == sum(g["steps"] for g in games) >= 6000
 
