@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the equity hot path (BASELINE.json: "showdown evals/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg4|cfg1] [--deal uniform|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--deal uniform|reference]
     python bench.py --impl reference ...        # the reference's own C++ calculator on the host cores (oracle/_ref)
     torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU)
 
@@ -12,6 +12,8 @@ A "step" is one pass of the hot path over one batch of synthetic queries:
   cfg4: 169 starting-hand classes x 1,000,000 trials x 9 players, trials split over the ranks (strong scaling) and the
        [169,2] win/tie counters all-reduced with NCCL inside the timed step.
   cfg1: one heads-up preflop query x 10,000 trials (latency case).
+  cfg2: the exact kernels -- enumeration of 4,096 turn + 4,096 river spots, rank ids of 64 M hands (HBM roofline).
+  cfg5: 65,536 six-max tables in self-play, one action per table and step, get_equity (1,000 runs) for every action.
 `value` = showdown evals (trials x players, all ranks) / device time of the K steps (CUDA events, max over ranks), with
 the queries already resident in HBM.  `e2e` = the same metric through the host-buffer API (equity_counts_batch ->
 npk_equity_host): queries start in host memory, H2D + kernels + D2H inside the timed region.
