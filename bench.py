@@ -453,9 +453,20 @@ def main():
         npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5000 + i, deal_mode=args.deal)
     if world > 1:
         dist.barrier()
+    pinned = [torch.as_tensor(x).pin_memory() for x in (hole_h, board_h, npl_h)]
     e0 = time.perf_counter()
     for i in range(e2e_steps):
-        r = npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=args.deal)
+        if by_trial:
+            # a trial shard of a larger job: host queries -> device, this rank's trial range, NCCL all-reduce of the
+            # counters, totals back to the host (the host-buffer C entry point has no trial offset)
+            h, b_, n_ = (x.to(dev, non_blocking=True) for x in pinned)
+            both.zero_()
+            npk.get_equity_batch(h, b_, n_, t_cnt, seed_value=6000 + i, deal_mode=args.deal, trial_offset=t_off,
+                                 uniform_shape=(P, B), validate=False, out=out)
+            npk.dist.allreduce_counts(both)
+            r = both.cpu()
+        else:
+            r = npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=args.deal)
     e2e_s = time.perf_counter() - e0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -499,7 +510,9 @@ def main():
                    "wall_s_timed_loop": wall},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * Q), "d2h_bytes_per_step": int(16 * Q),
-                "steps": e2e_steps, "api": "neuron_poker_b200.equity_counts_batch -> npk_equity_host"},
+                "steps": e2e_steps,
+                "api": ("pinned host queries -> get_equity_batch(trial shard) -> NCCL all-reduce -> host" if by_trial
+                        else "neuron_poker_b200.equity_counts_batch -> npk_equity_host")},
         "gpu_launches": args.steps,
         "get_equity_calls_per_s": calls,
         "roofline": {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tthread-instr/s",
