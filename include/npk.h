@@ -96,6 +96,18 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
                      int deal_mode, uint32_t flags, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
                      void* workspace, void* stream);
 
+/*
+ * The same for MIXED batches without any host round trip (self-play loops, CUDA-graph capture): the queries are classified
+ * by shape on the device, and one kernel per shape named in `shape_mask` (bit (players-1)*6 + known_board_cards) is
+ * enqueued; each reads the size of its group from device memory and leaves at once when the batch holds no query of its
+ * shape.  Queries whose shape is not in the mask, or that are invalid, are left untouched (their counters stay as they
+ * are); nothing is validated or reported.  Results are identical to npk_equity_batch.
+ */
+int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                           uint64_t shape_mask, uint64_t seed, int64_t trial_offset, int64_t query_offset, int deal_mode,
+                           uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
+                           void* stream);
+
 /* HOST buffers in, HOST buffers out: copies the queries to the device (pinned staging owned by the library), runs
  * npk_equity_batch with validation, copies the counters back and returns when they are valid.  wins/ties (and the
  * optional win_types [Q,9], passes [Q]) are overwritten. */

@@ -44,6 +44,8 @@ def lib():
                 L.npk_equity_workspace_bytes.restype = i64
                 L.npk_equity_batch.argtypes = [u8, u8, u8, i64, i64, i32, i32, ctypes.c_uint64, i64, i64, i32,
                                                ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
+                L.npk_equity_batch_async.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, ctypes.c_uint64, i64, i64, i32,
+                                                     u64, u64, u64, u64, vp, vp]
                 L.npk_equity_host.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, i32, u64, u64, u64, u64]
                 L.npk_equity_ranges_batch.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i64, i64, i32,
                                                       ctypes.c_uint32, u64, u64, u64, u64, vp, vp]

@@ -91,9 +91,12 @@ int current_state(DeviceState** out)
 }
 
 // ---- query classification (mixed player counts / board sizes) --------------------------------------------------------
-// workspace layout (bytes): [0,512) 64 work counters u64 | [512,768) 64 group counts u32 | [768,1024) 64 cursors u32
-//                           | [1024,1028) invalid-query count | [1028,1032) range abort flag | [2048, 2048+4Q) qindex
-constexpr int kWsCounters = 0, kWsCounts = 512, kWsCursors = 768, kWsInvalid = 1024, kWsAbort = 1028, kWsIndex = 2048;
+// workspace layout (bytes): [0,512) 64 work counters u64 | [512,768) 64 group counts u32 | [768,1024) 64 group offsets u32
+//                           (exclusive prefix of the counts, sync-free mixed batches; a kernel reads its group as
+//                           {count = group[0], offset = group[64]}) | [1024,1028) invalid-query count
+//                           | [1028,1092) abort flag + diagnostics | [1280,1536) 64 fill cursors u32 | [2048, 2048+4Q) qindex
+constexpr int kWsCounters = 0, kWsCounts = 512, kWsOffsets = 768, kWsInvalid = 1024, kWsAbort = 1028, kWsCursors = 1280,
+              kWsIndex = 2048;
 constexpr int kGroups = 60;   // group = nopp * 6 + known, nopp 0..9, known 0..5
 
 __device__ __forceinline__ int classify_query(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
@@ -131,6 +134,30 @@ __global__ void classify_count_kernel(const uint8_t* hole, const uint8_t* board,
 }
 
 struct GroupOffsets { uint32_t off[64]; };
+
+// sync-free mixed batches: exclusive prefix of the group counts, written right behind them
+__global__ void group_offsets_kernel(uint8_t* ws)
+{
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + kWsOffsets);
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int g = 0; g < 64; g++) { offsets[g] = acc; acc += counts[g]; }
+    }
+}
+
+__global__ void classify_fill_dev_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
+                                         uint8_t* ws)
+{
+    uint32_t* cursors = reinterpret_cast<uint32_t*>(ws + kWsCursors);
+    const uint32_t* offsets = reinterpret_cast<const uint32_t*>(ws + kWsOffsets);
+    int32_t* qindex = reinterpret_cast<int32_t*>(ws + kWsIndex);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
+        const int g = classify_query(hole, board, n_players, q);
+        if (g < 0) continue;
+        qindex[offsets[g] + atomicAdd(&cursors[g], 1u)] = (int32_t)q;
+    }
+}
 
 __global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
                                      uint8_t* ws, GroupOffsets go)
@@ -410,6 +437,61 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
             if ((e = cudaEventRecord(ds->group_done[g], gs)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
             if ((e = cudaStreamWaitEvent(s, ds->group_done[g], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
         }
+    }
+    return NPK_OK;
+}
+
+int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                           uint64_t shape_mask, uint64_t seed, int64_t trial_offset, int64_t query_offset, int deal_mode,
+                           uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
+                           void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q < 0 || trials < 0 || trial_offset < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (Q == 0 || trials == 0) return NPK_OK;
+    if (Q > 0x7fffffffLL) return fail(NPK_ERR_INVALID_ARGUMENT, "at most 2^31-1 queries per call");
+    if (!hole || !board || !n_players || !wins_strict || !ties || !workspace)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+    shape_mask &= (1ull << kGroups) - 1ull;
+    if (!shape_mask) return fail(NPK_ERR_INVALID_ARGUMENT, "empty shape mask");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    cudaError_t e = cudaMemsetAsync(ws, 0, kWsIndex, s);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+    const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
+    classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
+    group_offsets_kernel<<<1, 32, 0, s>>>(ws);
+    classify_fill_dev_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
+
+    npk::EquityParams p{};
+    p.tables = ds->t;
+    p.hole = hole; p.board = board; p.n_players = n_players;
+    p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
+    p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
+    p.ties = reinterpret_cast<unsigned long long*>(ties);
+    p.win_types = reinterpret_cast<unsigned long long*>(win_types);
+    p.passes = deal_mode == NPK_DEAL_REFERENCE ? reinterpret_cast<unsigned long long*>(passes) : nullptr;
+    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+    p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);
+    p.qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
+    p.nq = 0;
+    const long long chunks = (trials + p.chunk - 1) / p.chunk;
+    const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
+    for (int g = 0; g < kGroups; g++) {
+        if (!(shape_mask >> g & 1ull)) continue;
+        p.group = counts + g;                    // {count, offset} of this shape, read by the kernel itself
+        p.work_counter = counters + g;
+        // the group's size is unknown on the host: every shape gets the whole chip, an empty one leaves at once
+        e = npk::launch_equity_uniform(g / 6, 5 - g % 6, p, Q * chunks, ds->sm_count, forced_warps, s);
+        if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
     }
     return NPK_OK;
 }

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
     constexpr int NBLK2 = (2 * NW + 3) / 4;   // Philox blocks per trial PAIR
     static_assert(D <= N, "not enough cards");
 
+    // sync-free mixed batches: the size of this shape's group and the start of its query list live in device memory
+    const long long nq = p.group ? (long long)p.group[0] : p.nq;
+    if (nq == 0) return;                                   // nothing of this shape in the batch: leave before staging
+    const int32_t* qindex = p.group ? p.qindex + p.group[64] : p.qindex;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
@@ -164,11 +168,11 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
     const uint32_t fy_addr = smem_u32(fy);
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
-    const long long n_items = p.nq * chunks;
+    const long long n_items = nq * chunks;
 
     for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
         const long long qslot = item / chunks, ci = item - qslot * chunks;
-        const long long q = p.qindex ? p.qindex[qslot] : qslot;
+        const long long q = qindex ? qindex[qslot] : qslot;
         const QueryStatic qs = load_query(p, q, KNOWN);
 
         __syncwarp();
@@ -333,6 +337,10 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
     constexpr int NBLK = (NS + 3) / 4;
     static_assert(D <= N, "not enough cards");
 
+    // sync-free mixed batches: the size of this shape's group and the start of its query list live in device memory
+    const long long nq = p.group ? (long long)p.group[0] : p.nq;
+    if (nq == 0) return;                                   // nothing of this shape in the batch: leave before staging
+    const int32_t* qindex = p.group ? p.qindex + p.group[64] : p.qindex;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(p.tables, smem + 128, bar));
@@ -343,11 +351,11 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
     const uint32_t fy_addr = smem_u32(fy);
 
     const long long chunks = (p.trials + p.chunk - 1) / p.chunk;
-    const long long n_items = p.nq * chunks;
+    const long long n_items = nq * chunks;
 
     for (long long item = next_item(p.work_counter, lane); item < n_items; item = next_item(p.work_counter, lane)) {
         const long long qslot = item / chunks, ci = item - qslot * chunks;
-        const long long q = p.qindex ? p.qindex[qslot] : qslot;
+        const long long q = qindex ? qindex[qslot] : qslot;
         const QueryStatic qs = load_query(p, q, KNOWN);
         const uint64_t avail0 = ~qs.known & ((1ull << 52) - 1ull);
 

@@ -31,6 +31,8 @@ struct EquityParams {
     const uint8_t* board;         // [Q,5] card ids, 0xFF = not dealt yet (known cards first)
     const uint8_t* n_players;     // [Q]
     const int32_t* qindex;        // [nq] query ids handled by this launch, or null = 0..nq-1
+    const uint32_t* group;        // device {count, offset} of this launch's shape group (sync-free mixed batches), or null:
+                                  // then nq = group[0] and qindex starts at qindex + group[64]
     long long nq;
     long long trials;             // trials per query in this launch
     long long trial_offset;       // first trial number (sharding a query over launches / GPUs)

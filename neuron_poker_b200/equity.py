@@ -294,12 +294,24 @@ def _as_cuda_u8(x, device, shape_tail):
     return x
 
 
+def shape_mask(players, known_board_cards=(0, 3, 4, 5)):
+    """Bit mask of the (players, known board cards) shapes a sync-free mixed batch may contain."""
+    m = 0
+    for p in players:
+        for k in known_board_cards:
+            m |= 1 << ((int(p) - 1) * 6 + int(k))
+    return m
+
+
 def get_equity_batch(hole, board, n_players, trials, seed_value=0, deal_mode="uniform", trial_offset=0, device=None,
-                     uniform_shape=None, validate=True, win_types=False, passes=False, out=None, query_offset=0):
+                     uniform_shape=None, validate=True, win_types=False, passes=False, out=None, query_offset=0,
+                     shapes=None):
     """Monte-Carlo counts for a batch of queries on the GPU (asynchronous on the current torch stream).
 
     hole [Q,2], board [Q,5] (0xFF padding), n_players [Q]: uint8 torch tensors (or array-likes, copied to the device).
     uniform_shape=(players, known_board_cards) promises every query has that shape (no classification round trip).
+    shapes=shape_mask(...) runs a MIXED batch without any host round trip: the shapes are sorted out on the device and
+    one kernel per shape in the mask is enqueued (npk_equity_batch_async); queries of other shapes are skipped.
     trial_offset / query_offset shift the Philox counters, so shards of a larger job reproduce its exact numbers.
     Returns dict of int64 CUDA tensors: wins [Q], ties [Q] (+ win_types [Q,9], passes [Q]); the counters are u64 on
     the device and viewed as int64.  `out` may hold preallocated zeroed tensors to accumulate into.
@@ -320,6 +332,16 @@ def get_equity_batch(hole, board, n_players, trials, seed_value=0, deal_mode="un
         ws = torch.empty(int(L.npk_equity_workspace_bytes(Q)), dtype=torch.uint8, device=dev)
         up, uk = (-1, -1) if uniform_shape is None else (int(uniform_shape[0]), int(uniform_shape[1]))
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if shapes is not None and uniform_shape is None:
+            _lib.check(L.npk_equity_batch_async(hole.data_ptr(), board.data_ptr(), n_players.data_ptr(), Q, int(trials),
+                                                ctypes.c_uint64(int(shapes)), ctypes.c_uint64(int(seed_value) & (2**64 - 1)),
+                                                int(trial_offset), int(query_offset), _DEAL[deal_mode],
+                                                out["wins"].data_ptr(), out["ties"].data_ptr(),
+                                                out["win_types"].data_ptr() if win_types else None,
+                                                out["passes"].data_ptr() if passes else None, ws.data_ptr(), stream))
+            ws.record_stream(torch.cuda.current_stream(dev))
+            out["trials"] = int(trials)
+            return out
         _lib.check(L.npk_equity_batch(hole.data_ptr(), board.data_ptr(), n_players.data_ptr(), Q, int(trials), up, uk,
                                       ctypes.c_uint64(int(seed_value) & (2**64 - 1)), int(trial_offset),
                                       int(query_offset), _DEAL[deal_mode], _lib.NPK_FLAG_VALIDATE if validate else 0,

@@ -204,11 +204,15 @@ class HoldemTables(object):
         self.decisions += 1
         return actions
 
-    def selfplay_step(self, agents, runs=1000, deal_mode="reference", restart_finished=True):
+    def selfplay_step(self, agents, runs=1000, deal_mode="reference", restart_finished=True, sync_free=False):
         """One action on every table, entirely on the device: the equity query of every current player
         (env.py:262-264: 1,000 runs, all players alive), the Monte-Carlo kernels, the agents' decisions
-        (agent_consider_equity / random) and the state machine.  Returns the actions taken (int8 CUDA tensor)."""
-        from .equity import get_equity_batch
+        (agent_consider_equity / random) and the state machine.  Returns the actions taken (int8 CUDA tensor).
+        sync_free=True sorts the queries by shape on the device and enqueues a kernel for every shape a table can ask
+        for (no host round trip at all: the step can be captured in a CUDA graph); the default reads the shape counts
+        back once per step and launches only the shapes present, side by side, which is faster (1.5 vs 2.1 ms for 65,536
+        tables on a B200)."""
+        from .equity import get_equity_batch, shape_mask
         hole, board, npl, _ = self.queries()
         out = getattr(self, "_mc_out", None)
         if out is None:
@@ -216,8 +220,10 @@ class HoldemTables(object):
                    "ties": self.torch.zeros(self.n_tables, dtype=self.torch.int64, device=self.device)}
             self._mc_out = out
         out["wins"].zero_(); out["ties"].zero_()
+        # sync_free: the shapes a table can ask for are 1 (inactive tables) .. n_players players, 0 / 3 / 4 / 5 board cards
         get_equity_batch(hole, board, npl, runs, seed_value=(self.seed << 20) + self.decisions, deal_mode=deal_mode,
-                         query_offset=self.table_offset, validate=False, out=out, device=self.device)
+                         query_offset=self.table_offset, validate=False, out=out, device=self.device,
+                         shapes=shape_mask(range(1, self.n_players + 1)) if sync_free else None)
         actions = self.decide(agents, wins=out["wins"], ties=out["ties"], runs=runs)
         self.step(actions, restart_finished=restart_finished)
         return actions

@@ -402,3 +402,30 @@ def test_one_query_fast_path_equals_the_batched_path(torch_mod):
                 if mode == "reference":
                     assert one["passes"] == int(two["passes"][0])
                 assert one["wins"] + one["ties"] <= runs
+
+
+def test_sync_free_mixed_batches_equal_the_classified_path(torch_mod):
+    """npk_equity_batch_async sorts a mixed batch by shape on the device and enqueues one kernel per shape of the mask
+    without any host round trip: same counters as the path that reads the shape counts back, in both dealing modes;
+    queries whose shape is not in the mask are left untouched."""
+    import neuron_poker_b200 as npk
+    from neuron_poker_b200.equity import shape_mask
+    rng = np.random.default_rng(11)
+    Q = 300
+    hole, board, npl = [], [], []
+    for q in range(Q):
+        known = [0, 3, 4, 5][rng.integers(0, 4)]
+        c = rng.permutation(52)[:2 + known].tolist()
+        hole.append(c[:2]); board.append(pad_board(c[2:])); npl.append(int(rng.integers(1, 8)))
+    hole, board, npl = (np.array(x, dtype=np.uint8) for x in (hole, board, npl))
+    for mode in ("uniform", "reference"):
+        a = npk.get_equity_batch(hole, board, npl, 777, seed_value=21, deal_mode=mode, win_types=True, passes=(mode == "reference"),
+                                 trial_offset=3, query_offset=9)
+        b = npk.get_equity_batch(hole, board, npl, 777, seed_value=21, deal_mode=mode, win_types=True, passes=(mode == "reference"),
+                                 trial_offset=3, query_offset=9, shapes=shape_mask(range(1, 8)))
+        for k in ("wins", "ties", "win_types") + (("passes",) if mode == "reference" else ()):
+            assert (a[k] == b[k]).all(), (mode, k)
+        c = npk.get_equity_batch(hole, board, npl, 777, seed_value=21, deal_mode=mode, shapes=shape_mask([2, 3]),
+                                 trial_offset=3, query_offset=9)
+        sel = torch_mod.as_tensor((npl == 2) | (npl == 3)).to(c["wins"].device)
+        assert (c["wins"][sel] == a["wins"][sel]).all() and (c["wins"][~sel] == 0).all() and (c["ties"][~sel] == 0).all()
