@@ -793,7 +793,7 @@ int npk_rank7_batch(const uint8_t* cards, int64_t N, uint16_t* ranks, void* stre
     int rc = current_state(&ds);
     if (rc) return rc;
     if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
-    cudaError_t e = npk::launch_rank7(ds->t, cards, N, ranks, grid_for(*ds, (N + 31) / 32, npk::kAuxThreads / 32),
+    cudaError_t e = npk::launch_rank7(ds->t, cards, N, ranks, grid_for(*ds, (N + 127) / 128, npk::kRank7Threads / 32),
                                       static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "rank7_kernel launch");
 }
@@ -836,7 +836,7 @@ int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uin
     if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
     if (maxp < 1 || maxp > 23) return fail(NPK_ERR_INVALID_ARGUMENT, "maxp must be 1..23");
     cudaError_t e = npk::launch_showdown(ds->t, holes, n_players, board, N, maxp, winner, wtype, ranks,
-                                         grid_for(*ds, (N + 31) / 32, npk::kAuxThreads / 32), static_cast<cudaStream_t>(stream));
+                                         grid_for(*ds, (N + 127) / 128, npk::kRank7Threads / 32), static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "showdown_kernel launch");
 }
 

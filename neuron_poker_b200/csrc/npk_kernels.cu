@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
 // all seven loads are issued before the first use, and the four rank ids leave as one 8-byte store.  HBM traffic is the
 // algorithmic 9 B per hand; the per-card work is one byte extract, one descriptor gather from shared memory, one add into
 // the key sum and the suit-counter update.
-__global__ void __launch_bounds__(kAuxThreads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
+__global__ void __launch_bounds__(kRank7Threads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
                                                                long long n, uint16_t* __restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1076,7 +1076,7 @@ cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long 
     size_t smem = aux_smem(t);
     cudaError_t e = cudaFuncSetAttribute(rank7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rank7_kernel<<<grid, kAuxThreads, smem, s>>>(t, cards, n, out);
+    rank7_kernel<<<grid, kRank7Threads, smem, s>>>(t, cards, n, out);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@ constexpr int kEquityMaxThreads = 512; // up to 16 warps per CTA, one CTA per SM
 constexpr size_t kMaxDynamicSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
 constexpr int kRefThreads = 512;       // generic range kernel
 constexpr int kAuxThreads = 512;
+constexpr int kRank7Threads = 1024;    // rank7 is latency-bound at one CTA per SM: 32 warps hide twice as much
 
 // State of the one-query fast path.  The counters live in device memory and are handed to the kernel as wins/ties/...;
 // the LAST warp to finish copies them into `host` (pinned, mapped host memory), zeroes them and the work counter for the
