@@ -192,7 +192,11 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
         uint32_t wins = 0, ties = 0;
         unsigned long long wt_pack = 0;
 
-        for (unsigned long long pb = a_begin >> 1; pb <= (a_end - 1) >> 1; pb += 32) {
+        // trial = 2 * pair + u is inside the item iff (trial - a_begin) < (a_end - a_begin) as UNSIGNED 32-bit numbers
+        // (an item holds at most 2,048 trials; a trial just below a_begin wraps around to a huge value)
+        const uint32_t span = (uint32_t)(a_end - a_begin);
+        uint32_t rel = (uint32_t)(2ull * (a_begin >> 1) - a_begin) + 2u * (uint32_t)lane;     // 2 * pair - a_begin
+        for (unsigned long long pb = a_begin >> 1; pb <= (a_end - 1) >> 1; pb += 32, rel += 64u) {
             const unsigned long long pair = pb + lane;
             uint32_t w[NBLK2 > 0 ? NBLK2 * 4 : 1];
 #pragma unroll
@@ -218,8 +222,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
             }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const unsigned long long trial = 2 * pair + u;
-                const bool active = trial >= a_begin && trial < a_end;
+                const bool active = rel + (uint32_t)u < span;
                 uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
 #pragma unroll
                 for (int k = 2 * NOPP; k < D; k++) { bsum += dv[u][k]; bcnt += suit_inc(dv[u][k]); }
