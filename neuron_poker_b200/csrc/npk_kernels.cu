@@ -682,12 +682,12 @@ __global__ void __launch_bounds__(kRank7Threads, 1) rank7_kernel(const DeviceTab
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
-    // descriptor of a card = per-rank word | suit << 4: the 13 per-rank words sit in 13 different banks, so this gather
-    // never conflicts (lanes with the same rank read the same word), unlike a 52-entry per-card table
-    uint32_t* s_rank = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
-    if (threadIdx.x < 13) s_rank[threadIdx.x] = tables.desc[4 * threadIdx.x];          // suit 0 of each rank
+    // per-card descriptor table in shared memory (a 13-word per-rank table would be conflict-free, but rebuilding the
+    // descriptor from rank and suit costs three more alu instructions per card, and this kernel is alu-bound: measured)
+    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
+    if (threadIdx.x < 52) s_desc[threadIdx.x] = tables.desc[threadIdx.x];
     __syncthreads();
-    auto card_desc = [&](uint32_t card) { return s_rank[card >> 2] | ((card & 3u) << 4); };
+    auto card_desc = [&](uint32_t card) { return s_desc[card]; };
     const bool aligned = ((reinterpret_cast<uintptr_t>(cards) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
     const long long quads = aligned ? n / 4 : 0;
     const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(cards);
