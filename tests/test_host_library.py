@@ -123,3 +123,68 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_reference_dealer_as_a_distribution_over_cards_is_exact():
+    """the reference's index-based dealer (montecarlo_python.py:165-189) and the card-based rule that
+    equity_refdeal_kernel implements -- uniform ordered pairs of distinct unseen cards minus the pairs whose second card
+    is the successor of the first, board cards uniform over the unseen cards minus their maximum -- are the SAME
+    distribution.  Exact enumeration with fractions on a nine-card deck: two opponents, then two board cards."""
+    from fractions import Fraction
+    from collections import defaultdict
+    deck = [3, 7, 8, 20, 21, 22, 40, 50, 51]
+
+    def reference(deck):
+        out = defaultdict(Fraction)
+
+        def opponents(r, k, prob, acc):
+            if k == 0:
+                return board(r, 2, prob, acc)
+            n = len(r)
+            valid = [(i1, i2) for i1 in range(n) for i2 in range(n - 1) if i1 != i2]
+            for i1, i2 in valid:
+                r2 = list(r)
+                c1 = r2.pop(i1)
+                c2 = r2.pop(i2)
+                opponents(r2, k - 1, prob / len(valid), acc + ((c1, c2),))
+
+        def board(r, k, prob, acc):
+            if k == 0:
+                out[acc] += prob
+                return
+            for j in range(len(r) - 1):                      # randint(0, len - 1): never the last element
+                r2 = list(r)
+                b = r2.pop(j)
+                board(r2, k - 1, prob / (len(r) - 1), acc + (b,))
+
+        opponents(list(deck), 2, Fraction(1), ())
+        return out
+
+    def card_rule(deck):
+        out = defaultdict(Fraction)
+
+        def opponents(avail, k, prob, acc):
+            if k == 0:
+                return board(avail, 2, prob, acc)
+            pairs = []
+            for c1 in avail:
+                above = [c for c in avail if c > c1]
+                succ = min(above) if above else None
+                pairs += [(c1, c2) for c2 in avail if c2 != c1 and c2 != succ]
+            for c1, c2 in pairs:
+                opponents(avail - {c1, c2}, k - 1, prob / len(pairs), acc + ((c1, c2),))
+
+        def board(avail, k, prob, acc):
+            if k == 0:
+                out[acc] += prob
+                return
+            cands = sorted(avail - {max(avail)})
+            for b in cands:
+                board(avail - {b}, k - 1, prob / len(cands), acc + (b,))
+
+        opponents(frozenset(deck), 2, Fraction(1), ())
+        return out
+
+    a, b = reference(deck), card_rule(deck)
+    assert sum(a.values()) == 1 and sum(b.values()) == 1
+    assert a == b and len(a) > 10000
