@@ -261,3 +261,125 @@ class HoldemTables(object):
     @staticmethod
     def legal_moves_list(mask):
         return [Action(a) for a in range(10) if int(mask) >> a & 1]
+
+
+# ---- one table with the reference's own front end ---------------------------------------------------------------------------
+class _Seat(object):
+    """What the reference calls PlayerShell (env.py:753-777), read from the device state."""
+
+    def __init__(self, agent, seat):
+        self.agent_obj, self.seat, self.name = agent, seat, getattr(agent, "name", "player")
+        self.stack, self.cards, self.equity_alive = None, [], float("nan")
+
+
+class HoldemTable(object):
+    """gym_env/env.py::HoldemTable for ONE table, state machine on the GPU: same constructor arguments, add_player(),
+    reset(), step(action) with the reference's return values (observation, reward, done, truncated, info), and the same
+    agent protocol -- an agent with an `autoplay` attribute is asked `agent.action(legal_moves, observation, info,
+    funds_history)` (agents/agent_consider_equity.py, agent_random.py plug in unchanged), any other seat is driven by
+    the `action` passed to step().  `get_equity` is the equity calculator of the plugin point (env.py:75-81); the default
+    is this package's get_equity.  funds_history is a list of stack rows instead of a pandas frame."""
+
+    def __init__(self, initial_stacks=100, small_blind=1, big_blind=2, render=False, funds_plot=True,
+                 max_raises_per_player_round=2, use_cpp_montecarlo=False, raise_illegal_moves=False, calculate_equity=False,
+                 get_equity=None, seed=0):
+        from .equity import get_equity as _gpu_equity, montecarlo as _gpu_montecarlo
+        self.get_equity = get_equity or (_gpu_montecarlo if use_cpp_montecarlo else _gpu_equity)
+        self.initial_stacks, self.small_blind, self.big_blind = initial_stacks, small_blind, big_blind
+        self.max_raises_per_player_round = max_raises_per_player_round
+        self.raise_illegal_moves = raise_illegal_moves
+        self.players, self.num_of_players = [], 0
+        self.tables, self.seed = None, seed
+        self.done, self.reward, self.info, self.observation, self.array_everything = False, None, None, None, None
+        self.funds_history, self.legal_moves, self.illegal_move_reward = [], [], -1
+
+    def add_player(self, agent):
+        """env.py:526-535"""
+        self.players.append(_Seat(agent, len(self.players)))
+        self.num_of_players += 1
+
+    # -- state mirrored from the device after every call --
+    def _pull(self):
+        from .cards import card_str
+        s = self.tables.state()[0]
+        self._s = s
+        n = self.num_of_players
+        for i, p in enumerate(self.players):
+            p.stack = float(s["stack"][i])
+            p.cards = [card_str(c) for c in s["cards"][i] if c < 52]
+        self.stage = Stage(int(s["stage"]))
+        self.done = bool(s["done"])
+        self.winner_ix = int(s["winner_ix"]) if s["winner_ix"] >= 0 else None
+        self.dealer_pos = int(s["dealer_pos"])
+        self.community_pot, self.current_round_pot = float(s["community_pot"]), float(s["current_round_pot"])
+        self.min_call = float(s["min_call"])
+        self.player_pots = [float(x) for x in s["player_pots"][:n]]
+        self.table_cards = [card_str(c) for c in s["table_cards"] if c < 52]
+        self.legal_moves = HoldemTables.legal_moves_list(s["legal_moves"])
+        cp = int(s["current_player"])
+        self.current_player = self.players[cp] if cp >= 0 else None
+        if int(s["funds_rows"]) > len(self.funds_history):
+            self.funds_history.append([float(x) for x in s["funds_last"][:n]])
+
+    def _get_environment(self):
+        """env.py:232-278: equity of the current player, observation vector, info dictionary."""
+        import torch
+        s, cp = self._s, self.current_player
+        alive = int(s["alive"][:self.num_of_players].sum())
+        eq = float("nan")
+        if cp is not None and len(cp.cards) == 2:
+            eq = self.get_equity(set(cp.cards), set(self.table_cards), alive, 1000)
+            cp.equity_alive = eq
+        obs = self.tables.observe(torch.tensor([eq], dtype=torch.float64, device=self.tables.device))[0].cpu().numpy()
+        self.array_everything = self.observation = obs
+        unit = self.big_blind * 100
+        self.info = {"player_data": {"position": cp.seat if cp else None, "equity_to_river_alive": eq,
+                                     "equity_to_river_2plr": float("nan"), "equity_to_river_3plr": float("nan"),
+                                     "stack": [p.stack / unit for p in self.players]},
+                     "community_data": {"stage": [i == min(self.stage.value, 3) for i in range(4)],
+                                        "community_pot": self.community_pot / unit,
+                                        "current_round_pot": self.current_round_pot / unit,
+                                        "big_blind": self.big_blind, "small_blind": self.small_blind,
+                                        "legal_moves": [a in self.legal_moves for a in Action]},
+                     "stage_data": self.tables.stage_data[0].cpu().numpy(), "legal_moves": self.legal_moves}
+
+    def _autoplay(self):
+        return self.current_player is not None and hasattr(self.current_player.agent_obj, "autoplay")
+
+    def reset(self, seed=None, options=None):
+        """env.py:138-168"""
+        if seed is not None:
+            self.seed = seed
+        if not self.players:
+            return self.array_everything, self.info
+        self.tables = HoldemTables(1, n_players=self.num_of_players, initial_stacks=self.initial_stacks,
+                                   small_blind=self.small_blind, big_blind=self.big_blind,
+                                   max_raises_per_player_round=self.max_raises_per_player_round,
+                                   autoplay=[int(hasattr(p.agent_obj, "autoplay")) for p in self.players], seed=self.seed)
+        self.tables.enable_observations()
+        self.funds_history = []
+        self._pull()
+        self._get_environment()
+        if self._autoplay() and not self.done:
+            self.step("initial_player_autoplay")
+        return self.array_everything, self.info
+
+    def _apply(self, action):
+        action = Action(int(getattr(action, "value", action)))
+        if action not in self.legal_moves:
+            if self.raise_illegal_moves:
+                raise ValueError("%s is an Illegal move, try again. Currently allowed: %s" % (action, self.legal_moves))
+        self.reward = float(self.tables.step([int(action)])[0].item())
+        self._pull()
+        self._get_environment()
+
+    def step(self, action):
+        """env.py:170-200: autoplay agents act until a seat driven from outside is to move (or the game is over)."""
+        self.reward = 0
+        if self._autoplay():
+            while self._autoplay() and not self.done and self.legal_moves:
+                a = self.current_player.agent_obj.action(self.legal_moves, self.observation, self.info, self.funds_history)
+                self._apply(a)
+        else:
+            self._apply(action)
+        return self.array_everything, self.reward, self.done, False, self.info

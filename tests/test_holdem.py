@@ -308,3 +308,54 @@ def test_selfplay_conserves_chips_and_finishes_games(cuda_device):
         tb.reset_done()
     assert finished > 0
     assert (tb.state()["hands_played"] > 0).all()
+
+
+@pytest.mark.gpu
+def test_single_table_front_end_runs_the_reference_agent_protocol(cuda_device):
+    """holdem.HoldemTable: the reference's env front end for one table.  Agents written against the reference's protocol
+    (an `autoplay` attribute and action(legal_moves, observation, info, funds_history), agents/agent_consider_equity.py)
+    drive a whole game; a seat without `autoplay` is driven through step(action) like the reference's tests do."""
+    from neuron_poker_b200.holdem import Action, HoldemTable, Stage
+
+    class EquityPlayer:                                   # agents/agent_consider_equity.py:21-58, same decisions
+        def __init__(self, name, min_call_equity, min_bet_equity):
+            self.name, self.min_call_equity, self.min_bet_equity, self.autoplay = name, min_call_equity, min_bet_equity, True
+            self.seen = 0
+
+        def action(self, action_space, observation, info, funds_history):
+            eq = info["player_data"]["equity_to_river_alive"]
+            assert 0.0 <= eq <= 1.0 and len(observation) == 22 + 51 * 3
+            self.seen += 1
+            if eq > self.min_bet_equity + .2 and Action.ALL_IN in action_space:
+                return Action.ALL_IN
+            if eq > self.min_bet_equity + .1 and Action.RAISE_2POT in action_space:
+                return Action.RAISE_2POT
+            if eq > self.min_bet_equity and Action.RAISE_POT in action_space:
+                return Action.RAISE_POT
+            if eq > self.min_bet_equity - .1 and Action.RAISE_HALF_POT in action_space:
+                return Action.RAISE_HALF_POT
+            if eq > self.min_call_equity and Action.CALL in action_space:
+                return Action.CALL
+            return Action.CHECK if Action.CHECK in action_space else Action.FOLD
+
+    env = HoldemTable(initial_stacks=20, seed=3)
+    agents = [EquityPlayer("a", .5, .7), EquityPlayer("b", .2, .9), EquityPlayer("c", .4, .6)]
+    for a in agents:
+        env.add_player(a)
+    env.reset()                                            # all seats autoplay: reset() plays the whole game (env.py:165-166)
+    assert env.done and sum(a.seen for a in agents) > 3
+    assert abs(sum(p.stack for p in env.players) - 60) < 1e-9 and len(env.funds_history) >= 2
+
+    class Human:                                          # reference tests/test_gym_env.py::PlayerForTest
+        name = "h"
+
+    env = HoldemTable(seed=4)
+    for _ in range(6):
+        env.add_player(Human())
+    obs, info = env.reset()
+    assert env.current_player.seat == 3 and env.stage == Stage.PREFLOP and len(obs) == 328
+    obs, reward, done, truncated, info = env.step(Action.CALL)
+    assert env.current_player.seat == 4 and env.players[3].stack == 98 and not done and truncated is False
+    assert 0.0 <= info["player_data"]["equity_to_river_alive"] <= 1.0
+    env.step(Action.CHECK)                                # illegal here: costs -1, nothing else happens
+    assert env.reward == -1 and env.current_player.seat == 4
