@@ -31,29 +31,35 @@ def stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile libnpk.so if missing or older than its sources.  Returns the library path."""
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile libnpk.so if missing or older than its sources.  Returns the library path.
+    `defines` / `out` build an experimental variant next to it (tools/: kernel experiments select it with NPK_LIBRARY)."""
+    if not force and not stale() and out is None:
         return LIB
     objs = []
     procs = []
+    tag = "" if out is None else "_" + os.path.splitext(os.path.basename(out))[0]
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(HERE, "build", os.path.splitext(src)[0] + tag + ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for cmd, pr in procs:
-        out, _ = pr.communicate()
-        if verbose and out:
-            print(out)
+        log, _ = pr.communicate()
+        if verbose and log:
+            print(log)
         if pr.returncode:
-            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), out))
-    link = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+            raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), log))
+    target = LIB if out is None else out
+    link = [_nvcc(), "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(link)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

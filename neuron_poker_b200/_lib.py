@@ -29,9 +29,11 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                path = _build.LIB
-                if not os.path.exists(path) or (_build.stale() and os.environ.get("NPK_NO_REBUILD") != "1"):
-                    path = _build.build()
+                path = os.environ.get("NPK_LIBRARY")            # an experimental build (tools/), never a fallback
+                if not path:
+                    path = _build.LIB
+                    if not os.path.exists(path) or (_build.stale() and os.environ.get("NPK_NO_REBUILD") != "1"):
+                        path = _build.build()
                 L = ctypes.CDLL(path)
                 vp, u8, u16, u32, u64, i64, i32 = (ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                     ctypes.c_void_p, ctypes.c_int64, ctypes.c_int)

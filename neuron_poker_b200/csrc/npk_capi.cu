@@ -180,7 +180,7 @@ uint32_t pick_chunk(long long queries, long long trials, int sm_count, int lanes
     const long long warps = (long long)sm_count * 16;
     long long c = (queries * trials) / (8 * warps);
     if (getenv("NPK_CHUNK")) c = atoll(getenv("NPK_CHUNK"));      // tuning aid
-    c = (c + lanes_worth - 1) / lanes_worth * lanes_worth;      // a warp iteration covers 32 trials (K1': one per lane) or 64 (K1: a pair per lane)
+    c = (c + lanes_worth - 1) / lanes_worth * lanes_worth;      // a warp iteration covers 64 trials (a pair per lane)
     if (c < lanes_worth) c = lanes_worth;
     if (c > 2048) c = 2048;
     if (trials <= c) return (uint32_t)(trials > 0 ? trials : 1);
@@ -351,7 +351,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count, 64);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
@@ -472,7 +472,7 @@ int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
+    p.chunk = pick_chunk(Q, trials, ds->sm_count, 64);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
@@ -552,7 +552,7 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
         for (int i = 0; i < 5; i++) p.inline_query |= (uint64_t)board[i] << (16 + 8 * i);
         p.nq = 1; p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
         p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-        p.chunk = pick_chunk(1, trials, ds->sm_count, deal_mode == NPK_DEAL_REFERENCE ? 32 : 64);
+        p.chunk = pick_chunk(1, trials, ds->sm_count, 64);
         p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
         p.single = ds->single;
         p.work_counter = &ds->single->work_counter;

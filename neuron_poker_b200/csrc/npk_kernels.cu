@@ -265,26 +265,32 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
 }
 
 // =====================================================================================================================
-// K1': the Python reference's dealer (tools/montecarlo_python.py:165-189), shape-specialised like K1.
+// K1': the Python reference's dealer (tools/montecarlo_python.py:165-189), shape-specialised like K1, REJECTION-FREE.
 //
-// What the reference does, on the ORDERED list R of unseen cards (n of them):
+// What the reference does, on the ORDERED list R of unseen cards (n of them, ascending card id):
 //   opponent: i1 ~ U[0,n), i2 ~ U[0,n-1), retry while i1 == i2;  c1 = R.pop(i1); c2 = R.pop(i2)                  (:169-179)
-//   board:    j ~ U[0, n-1);  c = R.pop(j)  -- the highest unseen card never reaches the board                    (:188)
-// Seen as a distribution over cards: (c1, c2) is a uniformly drawn ordered pair of distinct unseen cards, redrawn
-// whenever c2 is the SUCCESSOR of c1 in R (pop(i1) moves R[i1+1] to index i1, so i2 == i1 is exactly that pair; every
-// state has (n-1)^2 admissible pairs and each attempt fails with probability 1/n, which is the distribution of the
-// reference's `passes`); a board card is uniform over R without its maximum.  That needs no ordered list: the cards are
-// drawn from K1's conflict-free shared-memory deck (partial Fisher-Yates, same four shared-memory operations per card),
-// and a 52-bit availability mask in two registers answers "successor of c1" and "maximum of R".  The two excluded
-// outcomes are rare (1/n each), so the retry loops are entered only when some lane of the warp needs them.
+//   board:    j ~ U[0, n-1);  c = R.pop(j)  -- the last element of R never reaches the board                      (:188)
+// The accepted (i1, i2) are uniform over {i1 in [0,n), i2 in [0,n-1), i1 != i2}: (n-1)^2 pairs.  For a fixed i2 = b the
+// admissible i1 are [0,n) without b, so  (a, b) uniform in [0,n-1)^2  ->  (i1, i2) = (a + (a >= b), b)  is a bijection
+// onto the accepted set: the retry loop disappears and a trial is D = 2*NOPP + NB pops at known indices -- a Lehmer code.
+// Decoding it needs no ordered list either.  Walking the pops BACKWARDS, un-popping pop k shifts every later pop whose
+// index is >= i_k up by one; after the sweep every index is a slot of the CANONICAL (ascending, never modified) deck.
+// The sweep is SIMD inside registers: four 8-bit indices per register, and for bytes x, t < 64 bit 7 of x + (0x80 - t)
+// says x >= t, so  tmp = x4 + C_k;  x4 += (tmp & H) >> 7  bumps up to four later pops with three instructions
+// (IADD3, LOP3, IMAD.HI -- C_k = 0x80808080 - i_k * 0x01010101 from the raw index, H = 0x80 in the bytes j > k).
+// The card descriptors are then read from the warp's lane-interleaved copy of the canonical deck: ONE conflict-free LDS
+// per card, no STS, no restore (K1's shuffle needs two LDS + two STS per card), no card ids, no availability mask, no
+// divergence.  Round 1 drew from K1's shuffled deck and rejected on card ids: 830 executed instructions per trial, lane
+// efficiency 25 of 32 (profiles/r01_ncu_refdeal_v1.txt).
 //
-// Random numbers: draw slot s (opponents, then board cards) consumes word s of the Philox4x32-10 stream with counter
-// (trial, query, 0x80000000 + block), key = seed; an opponent's word gives both indices (i1 = hi32(w*n), i2 =
-// hi32(lo32(w*n)*(n-1))).  Retry r = 1, 2, ... of a slot draws from fmix32(w + r * 0x9E3779B9) (the 32-bit murmur3
-// finaliser, a bijection, applied to a counter -- an ITERATED map x -> fmix32(x + c) has fixed points, and one whose
-// indices are (4, 5) of the sorted deck rejects forever: found on the B200 in round 1) instead of a fresh counter block:
-// retries happen in 2 % of the draws, a block per retry would cost more than the rest of the trial.  A trial is still
-// a pure function of (seed, query, trial); a slot that exhausts kMaxRangeAttempts retries raises p.abort_flag.
+// Random numbers: Philox4x32-10, key = seed.  A trial needs NWR = NOPP + ceil(NB/2) words: word o gives opponent o's
+// (a, b) by multiply-shift with remainder reuse (a = hi32(w*(n-1)), b = hi32(lo32(w*(n-1))*(n-1))), a board word serves two
+// board cards the same way.  Trials are generated in PAIRS like K1's: pair P = trial >> 1 draws ceil(2*NWR/4) blocks with
+// counter (P_lo, P_hi, query, 0x80000000 + block); trial 2P reads words [0, NWR), trial 2P+1 words [NWR, 2*NWR).
+// `passes` (the reference's count of draw attempts, :167) is a by-product of ITS rejection loop: an attempt fails with
+// probability 1/n, independently of the pair finally dealt.  When the caller asks for it, it is drawn from that law
+// (1 + a geometric number of failures per opponent) out of a separate block (counter 0x40000000 + ...), so the joint
+// distribution of (cards, passes) is the reference's.
 // =====================================================================================================================
 struct WordStream {
     uint32_t c0, c1, c2, k0, k1, blk, have;
@@ -314,20 +320,86 @@ __device__ __forceinline__ int select_bit(uint64_t m, int k)
     return base;
 }
 
-__device__ __forceinline__ uint32_t fmix32(uint32_t x)
+// NPK_IMAD_LEVEL (experiment, kept for the record): multipliers read from constant memory stop ptxas from strength-reducing
+// the multiply-adds below into LEA / SHF / IADD3 (alu pipe) and keep them on the fma pipe (IMAD).  Measured on B200, cfg3
+// with the reference's dealer: level 0 (ptxas decides: SHF + IMAD.IADD) 380 G evals/s, level 1 (pack / unpack / shift as
+// IMAD) 352 G, level 2 (the add of the bump as IMAD too) 349 G -- ptxas balances the two pipes better than a fixed rule.
+#ifndef NPK_IMAD_LEVEL
+#define NPK_IMAD_LEVEL 0
+#endif
+__constant__ uint32_t c_mul[12] = {1u, 256u, 65536u, 1u << 24, 1u << 25, 128u, 1u << 31, 1u << 23, 1u << 15, 0u, 0u, 0u};
+
+__device__ __forceinline__ uint32_t imad_lo(uint32_t a, uint32_t b, uint32_t c)
 {
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-    return x;
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t imad_hi(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
 }
 
-// card id (4*rank + suit) of a descriptor: bits 0..3 hold 12 - rank, bits 4..5 the suit
-__device__ __forceinline__ uint32_t desc_card(uint32_t d) { return 48u - 4u * (d & 15u) + ((d >> 4) & 3u); }
-
-// is card `id2` the lowest unseen card above `id1`?  (avail holds both)
-__device__ __forceinline__ bool is_successor(uint64_t avail, uint32_t id1, uint32_t id2)
+// x4 + (((x4 + c) & h) >> 7): the byte-wise "bump" of the Lehmer sweep
+__device__ __forceinline__ uint32_t bump4(uint32_t x4, uint32_t c, uint32_t h)
 {
-    const uint64_t above = avail >> (id1 + 1u);
-    return above != 0 && id1 + (uint32_t)__ffsll((long long)above) == id2;
+#if NPK_IMAD_LEVEL >= 2
+    const uint32_t t = imad_lo(x4, c_mul[0], c) & h;
+#else
+    const uint32_t t = (x4 + c) & h;
+#endif
+#if NPK_IMAD_LEVEL >= 1
+    return imad_hi(t, c_mul[4], x4);
+#else
+    return x4 + (t >> 7);
+#endif
+}
+
+// Decode D pop indices (raw[k] < 64, pop k taken from the list shortened by pops 0..k-1) into canonical slots, packed
+// four per register.
+template <int D>
+__device__ __forceinline__ void lehmer_decode(const uint32_t (&raw)[D > 0 ? D : 1], uint32_t (&x4)[(D + 3) / 4 > 0 ? (D + 3) / 4 : 1])
+{
+    constexpr int G = (D + 3) / 4;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        uint32_t v = raw[4 * g];
+#pragma unroll
+        for (int b = 1; b < 4; b++)
+            if (4 * g + b < D) {
+#if NPK_IMAD_LEVEL >= 1
+                v = imad_lo(raw[4 * g + b], c_mul[b], v);
+#else
+                v += raw[4 * g + b] << (8 * b);
+#endif
+            }
+        x4[g] = v;
+    }
+#pragma unroll
+    for (int k = D - 2; k >= 0; k--) {
+        const uint32_t c = 0x80808080u - raw[k] * 0x01010101u;       // IMAD
+#pragma unroll
+        for (int g = (k + 1) / 4; g < G; g++) {
+            uint32_t h = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (4 * g + b > k && 4 * g + b < D) h |= 0x80u << (8 * b);
+            x4[g] = bump4(x4[g], c, h);
+        }
+    }
+}
+
+// shared address of slot j's descriptor in a lane-interleaved deck: base + 128 * byte (j & 3) of x4
+__device__ __forceinline__ uint32_t slot_addr(uint32_t x4, int b, uint32_t base)
+{
+    const uint32_t f = x4 & (0xFFu << (8 * b));
+#if NPK_IMAD_LEVEL >= 1
+    return b == 0 ? imad_lo(f, c_mul[5], base) : imad_hi(f, c_mul[5 + b], base);
+#else
+    return b == 0 ? base + f * 128u : base + (f >> (8 * b - 7));
+#endif
 }
 
 template <int NOPP, int NB>
@@ -336,8 +408,9 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
     constexpr int KNOWN = 5 - NB;
     constexpr int N = 50 - KNOWN;          // unseen cards
     constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
-    constexpr int NS = NOPP + NB;          // draw slots = Philox words per trial (before retries)
-    constexpr int NBLK = (NS + 3) / 4;
+    constexpr int NWR = NOPP + (NB + 1) / 2;       // Philox words per trial
+    constexpr int NBLK2 = (2 * NWR + 3) / 4;       // Philox blocks per trial PAIR
+    constexpr int G = (D + 3) / 4;
     static_assert(D <= N, "not enough cards");
 
     // sync-free mixed batches: the size of this shape's group and the start of its query list live in device memory
@@ -360,128 +433,102 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
         const long long qslot = item / chunks, ci = item - qslot * chunks;
         const long long q = qindex ? qindex[qslot] : qslot;
         const QueryStatic qs = load_query(p, q, KNOWN);
-        const uint64_t avail0 = ~qs.known & ((1ull << 52) - 1ull);
 
         __syncwarp();
-        for (int c = lane; c < 52; c += 32)
-            if (avail0 >> c & 1ull) scratch[__popcll(avail0 & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        {
+            const uint64_t avail = ~qs.known & ((1ull << 52) - 1ull);
+            for (int c = lane; c < 52; c += 32)
+                if (avail >> c & 1ull) scratch[__popcll(avail & ((1ull << c) - 1ull))] = p.tables.desc[c];
+        }
         __syncwarp();
 #pragma unroll 4
-        for (int j = 0; j < N; j++) fy[j * 32] = scratch[j];
+        for (int j = 0; j < N; j++) fy[j * 32] = scratch[j];       // read-only from here on: the canonical deck
         __syncwarp();
 
-        const long long t_begin = ci * p.chunk;
-        const long long t_end = min(p.trials, t_begin + (long long)p.chunk);
-        uint32_t wins = 0, ties = 0, passes = 0;        // passes <= 64 iterations * 9 opponents * a few attempts
+        const unsigned long long a_begin = (unsigned long long)(p.trial_offset + ci * p.chunk);
+        const unsigned long long a_end = (unsigned long long)(p.trial_offset + min(p.trials, (ci + 1) * (long long)p.chunk));
+        uint32_t wins = 0, ties = 0, passes = 0;        // passes <= 64 iterations * 2 * 9 opponents * a few attempts
         unsigned long long wt_pack = 0;
 
-        for (long long tb = t_begin; tb < t_end; tb += 32) {
-            const long long t_local = tb + lane;
-            const bool active = t_local < t_end;
-            const unsigned long long trial = (unsigned long long)(p.trial_offset + t_local);
-            uint32_t w[NBLK > 0 ? NBLK * 4 : 1];
+        const uint32_t span = (uint32_t)(a_end - a_begin);
+        uint32_t rel = (uint32_t)(2ull * (a_begin >> 1) - a_begin) + 2u * (uint32_t)lane;     // 2 * pair - a_begin
+        for (unsigned long long pb = a_begin >> 1; pb <= (a_end - 1) >> 1; pb += 32, rel += 64u) {
+            const unsigned long long pair = pb + lane;
+            uint32_t w[NBLK2 > 0 ? NBLK2 * 4 : 1];
 #pragma unroll
-            for (int b = 0; b < NBLK; b++)
-                philox4x32_10((uint32_t)trial, (uint32_t)(trial >> 32), (uint32_t)q + p.query_offset, 0x80000000u + (uint32_t)b,
+            for (int b = 0; b < NBLK2; b++)
+                philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)q + p.query_offset, 0x80000000u + (uint32_t)b,
                               p.seed_lo, p.seed_hi, &w[4 * b]);
-            uint32_t dv[D > 0 ? D : 1], slot[D > 0 ? D : 1];
-            uint64_t avail = avail0;
-            uint32_t tries = 0;
+            uint32_t dv[2][D > 0 ? D : 1];
 #pragma unroll
-            for (int o = 0; o < NOPP; o++) {
-                constexpr uint32_t kGold = 0x9E3779B9u;
-                const uint32_t n = (uint32_t)(N - 2 * o);
-                const uint32_t t1 = lds_u32(fy_addr + (n - 1u) * 128u), t2 = lds_u32(fy_addr + (n - 2u) * 128u);
-                const uint32_t w0 = w[o];
-                uint32_t x = w0, i1, i2, c1, c2, id1, id2;
-                bool ok;
-                auto attempt = [&]() {
-                    i1 = __umulhi(x, n);
-                    i2 = __umulhi(x * n, n - 1u);
-                    c1 = lds_u32(fy_addr + i1 * 128u);
-                    const uint32_t other = lds_u32(fy_addr + i2 * 128u);
-                    c2 = i2 == i1 ? t1 : other;               // the hole c1 leaves is filled with the last live card
-                    id1 = desc_card(c1); id2 = desc_card(c2);
-                    ok = !is_successor(avail, id1, id2);
-                    tries++;
-                };
-                attempt();
-                if (__any_sync(0xffffffffu, !ok)) {
-                    uint32_t guard = 0;
-#pragma unroll 1
-                    while (!ok) {
-                        x = fmix32(w0 + ++guard * kGold);          // retry r draws from fmix32(word + r * golden ratio)
-                        attempt();
-                        if (guard > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); break; }   // cannot happen: an attempt fails with probability 1/n
+            for (int u = 0; u < 2; u++) {
+                uint32_t raw[D > 0 ? D : 1];
+#pragma unroll
+                for (int o = 0; o < NOPP; o++) {
+                    const uint32_t m = (uint32_t)(N - 2 * o - 1);              // n - 1
+                    const uint32_t x = w[u * NWR + o];
+                    const uint32_t a = __umulhi(x, m), b = __umulhi(x * m, m);
+                    raw[2 * o] = a + (a >= b ? 1u : 0u);
+                    raw[2 * o + 1] = b;
+                }
+                uint32_t rem = 0;
+#pragma unroll
+                for (int c = 0; c < NB; c++) {
+                    const uint32_t m = (uint32_t)(N - 2 * NOPP - c - 1);       // n - 1: never the last element
+                    const uint32_t x = (c & 1) ? rem : w[u * NWR + NOPP + (c >> 1)];
+                    raw[2 * NOPP + c] = __umulhi(x, m);
+                    rem = x * m;
+                }
+                uint32_t x4[G > 0 ? G : 1];
+                lehmer_decode<D>(raw, x4);
+#pragma unroll
+                for (int k = 0; k < D; k++) dv[u][k] = lds_u32(slot_addr(x4[k >> 2], k & 3, fy_addr));
+            }
+            if (p.passes) {
+                // the reference's attempt counter: every opponent costs 1 + Geometric(1/n) attempts
+                constexpr int NPB = (2 * NOPP + 3) / 4;
+#pragma unroll
+                for (int b = 0; b < NPB; b++) {
+                    uint32_t pw[4];
+                    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)q + p.query_offset, 0x40000000u + (uint32_t)b,
+                                  p.seed_lo, p.seed_hi, pw);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int s = 4 * b + i;                                   // word s: trial s / NOPP, opponent s % NOPP
+                        if (s < 2 * NOPP) {
+                            const uint32_t n = (uint32_t)(N - 2 * (s % (NOPP > 0 ? NOPP : 1)));
+                            uint32_t x = pw[i], tries = 1;
+                            while (x < 0xFFFFFFFFu / n && tries < kMaxRangeAttempts) { tries++; x *= n; }   // x < 2^32 / n with probability 1/n
+                            if (rel + (uint32_t)(s / (NOPP > 0 ? NOPP : 1)) < span) passes += tries;
+                        }
                     }
                 }
-                slot[2 * o] = fy_addr + i1 * 128u; slot[2 * o + 1] = fy_addr + i2 * 128u;
-                dv[2 * o] = c1; dv[2 * o + 1] = c2;
-                sts_u32(slot[2 * o], t1);
-                sts_u32(slot[2 * o + 1], i1 == n - 2u ? t1 : t2);
-                avail &= ~((1ull << id1) | (1ull << id2));
-            }
-            // The highest unseen card never reaches the board (:188) -- and since it is never dealt there, it stays the
-            // highest for all NB board draws: find it once and compare the low six descriptor bits (suit, 12 - rank).
-            uint32_t top6 = 0xFFFFFFFFu;
-            if (NB > 0) {
-                const uint32_t top = 63u - (uint32_t)__clzll((long long)avail);
-                top6 = ((top & 3u) << 4) | (12u - (top >> 2));
             }
 #pragma unroll
-            for (int b = 0; b < NB; b++) {
-                constexpr uint32_t kGold = 0x9E3779B9u;
-                const uint32_t n = (uint32_t)(N - 2 * NOPP - b);
-                const uint32_t t1 = lds_u32(fy_addr + (n - 1u) * 128u);
-                const uint32_t w0 = w[NOPP + b];
-                uint32_t x = w0, i1, c1;
-                bool ok;
-                auto attempt = [&]() {
-                    i1 = __umulhi(x, n);
-                    c1 = lds_u32(fy_addr + i1 * 128u);
-                    ok = (c1 & 63u) != top6;
-                };
-                attempt();
-                if (__any_sync(0xffffffffu, !ok)) {
-                    uint32_t guard = 0;
-#pragma unroll 1
-                    while (!ok) {
-                        x = fmix32(w0 + ++guard * kGold);
-                        attempt();
-                        if (guard > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); break; }
-                    }
+            for (int u = 0; u < 2; u++) {
+                const bool active = rel + (uint32_t)u < span;
+                uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
+#pragma unroll
+                for (int k = 2 * NOPP; k < D; k++) { bsum += dv[u][k]; bcnt += suit_inc(dv[u][k]); }
+                const BoardFlush bf = board_flush(bcnt);
+                uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
+#pragma unroll
+                for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[u][k], bf.fsx);
+                const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
+                uint32_t best = 0;
+#pragma unroll
+                for (int o = 0; o < NOPP; o++) {
+                    const uint32_t d0 = dv[u][2 * o], d1 = dv[u][2 * o + 1];
+                    best = max(best, eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr));
                 }
-                slot[2 * NOPP + b] = fy_addr + i1 * 128u;
-                dv[2 * NOPP + b] = c1;
-                sts_u32(slot[2 * NOPP + b], t1);
-            }
+                const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
+                wins += win; ties += tie;
+                if (p.win_types && (win || tie)) {
+                    uint32_t ty = 0;
 #pragma unroll
-            for (int k = D - 1; k >= 0; k--) sts_u32(slot[k], dv[k]);
-            if (active) passes += tries;
-
-            uint32_t bsum = qs.board_sum, bcnt = qs.board_cnt;
-#pragma unroll
-            for (int k = 2 * NOPP; k < D; k++) { bsum += dv[k]; bcnt += suit_inc(dv[k]); }
-            const BoardFlush bf = board_flush(bcnt);
-            uint32_t bfield = prmt(qs.board_lo, qs.board_hi, bf.sel);
-#pragma unroll
-            for (int k = 2 * NOPP; k < D; k++) bfield |= flush_bit(dv[k], bf.fsx);
-
-            const uint32_t hv = eval_player(st, bsum + qs.hero_sum, bfield | prmt(qs.hero_lo, qs.hero_hi, bf.sel), bf.thr);
-            uint32_t best = 0;
-#pragma unroll
-            for (int o = 0; o < NOPP; o++) {
-                const uint32_t d0 = dv[2 * o], d1 = dv[2 * o + 1];
-                const uint32_t ov = eval_player(st, bsum + d0 + d1, bfield | flush_bit(d0, bf.fsx) | flush_bit(d1, bf.fsx), bf.thr);
-                best = max(best, ov);
-            }
-            const bool win = active && (NOPP == 0 || hv > best), tie = active && NOPP > 0 && hv == best;
-            wins += win; ties += tie;
-            if (p.win_types && (win || tie)) {
-                uint32_t ty = 0;
-#pragma unroll
-                for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
-                wt_pack += 1ull << (7 * ty);
+                    for (int i = 1; i < 9; i++) ty += hv >= p.tables.type_start[i];
+                    wt_pack += 1ull << (7 * ty);
+                }
             }
         }
 
@@ -492,7 +539,6 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
             atomicAdd(&p.ties[q], (unsigned long long)ties);
         }
         if (p.passes) {
-            // per-lane counts stay below 2^16 per item only in expectation: sum them in two halves
             const uint32_t plo = __reduce_add_sync(0xffffffffu, passes & 0xffffu);
             const uint32_t phi = __reduce_add_sync(0xffffffffu, passes >> 16);
             if (lane == 0) atomicAdd(&p.passes[q], (unsigned long long)plo + ((unsigned long long)phi << 16));

@@ -8,9 +8,8 @@ checked for bit-identical win / tie / pass / win-type counts -- not only statist
             draw k takes index hi32(x * (N-k)) where x is a fresh Philox word for even k and the low product word of
             the previous draw for odd k; the hole left by a draw is filled with the last live element.  Two consecutive
             trials share their Philox blocks (see deal_uniform).
-  reference (equity_refdeal_kernel): the Python reference's dealer, montecarlo_python.py:165-189, as a distribution
-            over cards -- uniform draws from the same deck, redrawn for the two outcomes the reference excludes (second
-            opponent card = successor of the first; board card = highest unseen card); see deal_reference().
+  reference (equity_refdeal_kernel): the Python reference's dealer, montecarlo_python.py:165-189 -- pops at random
+            indices of the ORDERED list of unseen cards, sampled without its retry loop; see deal_reference().
   ranges    (equity_ranges_kernel): the generic index-based dealer with class masks, see deal_ranges().
 """
 M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
@@ -71,76 +70,82 @@ class _Words:
         return self.buf.pop(0)
 
 
-GOLD = 0x9E3779B9
+PASSES_BLOCK0 = 0x40000000
+MAX_ATTEMPTS = 1 << 16
 
 
-def fmix32(x):
-    """32-bit murmur3 finaliser (a bijection): the retry stream of equity_refdeal_kernel."""
-    x ^= x >> 16
-    x = (x * 0x85EBCA6B) & MASK
-    x ^= x >> 13
-    x = (x * 0xC2B2AE35) & MASK
-    x ^= x >> 16
-    return x
+def lehmer_slots(raw):
+    """Canonical slots of a sequence of pops: raw[k] indexes the ordered list shortened by pops 0..k-1.  Restated the
+    way the kernel does it (backward sweep: un-popping pop k shifts every later pop >= raw[k] up by one)."""
+    s = list(raw)
+    for k in range(len(s) - 2, -1, -1):
+        for j in range(k + 1, len(s)):
+            if s[j] >= raw[k]:
+                s[j] += 1
+    return s
 
 
 def deal_reference(seed, query, trial, hole, board, players):
     """equity_refdeal_kernel.  Returns (opponent hands, full board, passes).
 
-    The reference's dealer (montecarlo_python.py:165-189) as a distribution over cards: an opponent gets a uniformly
-    drawn ordered pair of distinct unseen cards, redrawn while the second card is the SUCCESSOR of the first in the
-    ordered list of unseen cards (that is the reference's i1 == i2 retry after pop(i1)); a board card is uniform over
-    the unseen cards without their maximum (randint(0, n-1) never reaches the last list element).
-    Cards come from the same partial Fisher-Yates deck as the uniform dealer; draw slot s uses Philox word s of the
-    stream whose block counter starts at 0x80000000; retry r = 1, 2, ... of a slot draws from fmix32(word + r * 0x9E3779B9)."""
+    The reference's dealer (montecarlo_python.py:165-189) pops from the ORDERED list of unseen cards: an opponent takes
+    i1 in [0,n), i2 in [0,n-1), retried while i1 == i2 (:169-172), then pop(i1), pop(i2) (:178-179); a board card pops
+    index j in [0, n-1) (:188).  The accepted (i1, i2) are uniform over (n-1)^2 pairs, and (a, b) in [0,n-1)^2 ->
+    (a + (a >= b), b) is a bijection onto them: no retry.  Word o of the trial gives opponent o's a = hi32(w*(n-1)),
+    b = hi32(lo32(w*(n-1))*(n-1)); a board word serves two board cards (index = hi32(x*(n-1)), x = the word, then the low
+    product word).  Trials come in pairs sharing Philox blocks (counter (pair, query, 0x80000000 + block)), trial 2P reads
+    words [0, NWR), trial 2P+1 words [NWR, 2*NWR), NWR = opponents + ceil(board cards to come / 2).
+    `passes` is drawn from the law of the reference's attempt counter: per opponent 1 + a geometric number of failures
+    (an attempt fails with probability 1/n), from the pair's block(s) at counter 0x40000000 + block, word
+    (trial & 1) * opponents + o: failures = number of times x < floor((2^32-1)/n) holds along x -> x*n."""
     known = set(hole) | set(board)
     deck = [c for c in range(52) if c not in known]
-    avail = set(deck)
+    n0 = len(deck)
     nopp, nb = players - 1, 5 - len(board)
-    nblk = (nopp + nb + 3) // 4
+    nwr = nopp + (nb + 1) // 2
+    nblk = (2 * nwr + 3) // 4
     key = (seed & MASK, (seed >> 32) & MASK)
+    pair, half = trial >> 1, trial & 1
     w = []
     for b in range(nblk):
-        w += philox4x32_10((trial & MASK, (trial >> 32) & MASK, query & MASK, (REFERENCE_BLOCK0 + b) & MASK), key)
-    n = len(deck)
-    opp, passes = [], 0
+        w += philox4x32_10((pair & MASK, (pair >> 32) & MASK, query & MASK, (REFERENCE_BLOCK0 + b) & MASK), key)
+    w = w[half * nwr:(half + 1) * nwr]
+    raw = []
     for o in range(nopp):
-        x, r = w[o], 0
-        while True:
-            passes += 1
-            prod = x * n
-            i1, i2 = prod >> 32, ((prod & MASK) * (n - 1)) >> 32
-            c1 = deck[i1]
-            c2 = deck[n - 1] if i2 == i1 else deck[i2]
-            above = [c for c in avail if c > c1]
-            if not above or min(above) != c2:
-                break
-            r += 1
-            x = fmix32((w[o] + r * GOLD) & MASK)
-        deck[i1] = deck[n - 1]
-        deck[i2] = deck[i1] if i1 == n - 2 else deck[n - 2]       # deck[i1] now holds the old last card
-        avail -= {c1, c2}
-        n -= 2
-        opp.append([c1, c2])
-    full = list(board)
-    for b in range(nb):
-        x, r = w[nopp + b], 0
-        while True:
-            i1 = (x * n) >> 32
-            c1 = deck[i1]
-            if c1 != max(avail):
-                break
-            r += 1
-            x = fmix32((w[nopp + b] + r * GOLD) & MASK)
-        deck[i1] = deck[n - 1]
-        avail.discard(c1)
-        n -= 1
-        full.append(c1)
-    return opp, full, passes
+        m = n0 - 2 * o - 1
+        prod = w[o] * m
+        a, b = prod >> 32, ((prod & MASK) * m) >> 32
+        raw += [a + (1 if a >= b else 0), b]
+    rem = 0
+    for c in range(nb):
+        m = n0 - 2 * nopp - c - 1
+        x = rem if c & 1 else w[nopp + (c >> 1)]
+        prod = x * m
+        raw.append(prod >> 32)
+        rem = prod & MASK
+    cards = [deck[s] for s in lehmer_slots(raw)]
+    # cross-check against the literal list semantics of the reference
+    lst, lit = list(deck), []
+    for i in raw:
+        lit.append(lst.pop(i))
+    assert lit == cards
+    passes = 0
+    if nopp:
+        pw = []
+        for b in range((2 * nopp + 3) // 4):
+            pw += philox4x32_10((pair & MASK, (pair >> 32) & MASK, query & MASK, (PASSES_BLOCK0 + b) & MASK), key)
+        for o in range(nopp):
+            n = n0 - 2 * o
+            x, tries = pw[half * nopp + o], 1
+            while x < MASK // n and tries < MAX_ATTEMPTS:
+                tries += 1
+                x = (x * n) & MASK
+            passes += tries
+    opp = [cards[2 * i:2 * i + 2] for i in range(nopp)]
+    return opp, list(board) + cards[2 * nopp:], passes
 
 
 RANGES_BLOCK0 = {"reference": 0x80000000, "uniform": 0xC0000000}
-MAX_ATTEMPTS = 1 << 16
 
 
 def hand_class(c1, c2):

@@ -188,3 +188,22 @@ def test_reference_dealer_as_a_distribution_over_cards_is_exact():
     a, b = reference(deck), card_rule(deck)
     assert sum(a.values()) == 1 and sum(b.values()) == 1
     assert a == b and len(a) > 10000
+
+
+def test_reference_dealer_without_retries_is_the_reference_distribution():
+    """The rejection-free form equity_refdeal_kernel uses (tests/sampler_model.py::deal_reference): (a, b) uniform in
+    [0,n-1)^2 -> (i1, i2) = (a + (a >= b), b) hits every (i1, i2) the reference's retry loop accepts
+    (montecarlo_python.py:169-172: i1 in [0,n), i2 in [0,n-1), i1 != i2) exactly once; and the backward Lehmer sweep
+    yields the cards list.pop would."""
+    import random
+    import sampler_model as sm
+    for n in range(2, 12):
+        accepted = sorted((i1, i2) for i1 in range(n) for i2 in range(n - 1) if i1 != i2)
+        mapped = sorted((a + (1 if a >= b else 0), b) for a in range(n - 1) for b in range(n - 1))
+        assert mapped == accepted, n
+    rnd = random.Random(3)
+    for _ in range(300):
+        n, d = rnd.randint(24, 50), rnd.randint(0, 23)
+        raw = [rnd.randrange(n - k) for k in range(d)]
+        lst = list(range(n))
+        assert [lst.pop(i) for i in raw] == sm.lehmer_slots(raw)

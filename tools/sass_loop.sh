@@ -16,7 +16,7 @@ for i,l in enumerate(lines):
             j=addr.index(t) if t in addr else None
             if j is not None:
                 body=lines[j:i+1]
-                if any('STS' in b for b in body) and any('LDS.U16' in b for b in body):
+                if any('LDS.U16' in b for b in body) and len(body) > 150:
                     if best is None or (i-j)<best[1]-best[0]: best=(j,i)
 j,i=best
 c=collections.Counter()
