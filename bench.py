@@ -1,19 +1,22 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the equity hot path (BASELINE.json: "showdown evals/s").
+"""bench.py -- headline benchmark of the equity hot path (BASELINE.json: "showdown evals/s ...; get_equity calls/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg1|cfg2|cfg3|cfg4|cfg5] [--deal uniform|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # the driver's line: cfg3 headline + every other config
+    python bench.py --workload cfg1|cfg2|cfg3|cfg4|cfg5|ranges [--deal uniform|reference]    # one workload alone
     python bench.py --impl reference ...        # the reference's own C++ calculator on the host cores (oracle/_ref)
     torchrun --nproc-per-node N bench.py --gpus N ...   (one rank per GPU)
 
-A "step" is one pass of the hot path over one batch of synthetic queries:
-  cfg3 (default, the configuration the metric is quoted on): 4,096 six-player flop queries x 10,000 trials per GPU
-       = 245.76 M showdown evals per step per GPU.  N GPUs: every rank owns its own 4,096 queries (weak scaling, no
-       data-path collective; queries keep global ids in the Philox counter).
-  cfg4: 169 starting-hand classes x 1,000,000 trials x 9 players, trials split over the ranks (strong scaling) and the
-       [169,2] win/tie counters all-reduced with NCCL inside the timed step.
-  cfg1: one heads-up preflop query x 10,000 trials (latency case).
-  cfg2: the exact kernels -- enumeration of 4,096 turn + 4,096 river spots, rank ids of 64 M hands (HBM roofline).
-  cfg5: 65,536 six-max tables in self-play, one action per table and step, get_equity (1,000 runs) for every action.
+A "step" is one pass of the hot path over one batch of synthetic queries.  The headline (`value`, `e2e`, `roofline`) is
+  cfg3: 4,096 six-player flop queries x 10,000 trials per GPU = 245.76 M showdown evals per step per GPU; N GPUs: every
+        rank owns its own 4,096 queries (weak scaling, no data-path collective; global query ids in the Philox counter).
+The same JSON line carries, measured in the same run (BASELINE.json `configs`):
+  `sustained`  the cfg3 step looped for >= 3 s with its own clock samples (the K-step figure is a burst of a few ms)
+  `workloads`  cfg1 (one heads-up preflop call: latency, CPU vs GPU), cfg2 (exact enumeration + rank ids of 64 M hands
+               against the HBM roofline), cfg3 with the reference's dealer, cfg4 (169 classes x 1 M trials x 9 players,
+               trials split over the N ranks with the count all-reduce INSIDE the timed step: strong scaling, efficiency
+               against the unsharded job on one GPU, counters asserted bit-identical to the unsharded run on the device),
+               cfg5 (65,536 six-max tables in self-play, both dealers) and an opponent-range workload
+  `cpu_baseline`  the reference's C++, Python and numpy2 calculators on this box's host cores (N = 1 only)
 `value` = showdown evals (trials x players, all ranks) / device time of the K steps (CUDA events, max over ranks), with
 the queries already resident in HBM.  `e2e` = the same metric through the host-buffer API (equity_counts_batch ->
 npk_equity_host): queries start in host memory, H2D + kernels + D2H inside the timed region.
@@ -54,6 +57,9 @@ def workload(name):
     if name == "cfg1":
         return dict(name="cfg1: AsKs heads-up preflop x 10000 trials", queries=1, trials=10000, players=2, known=0,
                     shard="query")
+    if name == "ranges":
+        return dict(name="ranges: 4096 six-player flop queries x 1000 trials, opponents in the top 30 % of the reference's "
+                         "preflop ranking", queries=4096, trials=1000, players=6, known=3, shard="query")
     raise SystemExit("unknown workload " + name)
 
 
@@ -62,7 +68,7 @@ def make_queries(wl, world, rank):
     import numpy as np
     import torch
     q = wl["queries"]
-    if wl["name"].startswith("cfg3"):
+    if wl["name"].startswith("cfg3") or wl["name"].startswith("ranges"):
         g = torch.Generator().manual_seed(0)
         cards = torch.rand(q * world, 52, generator=g).argsort(1)[:, :5].to(torch.uint8).numpy()
         cards = cards[rank * q:(rank + 1) * q]
@@ -124,8 +130,8 @@ class ClockSampler(threading.Thread):
         self._halt.set()
         self.join(timeout=1)
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_min_mhz": s[0] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
 
 
 def host_cores():
@@ -135,6 +141,9 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs: the reference's own implementations on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
 def reference_sample(wl, hole, board, npl, n_queries, threads):
     """Time the reference's own C++ montecarlo() (oracle/_ref) on `n_queries` queries of the workload, `threads` threads."""
     import oracle
@@ -157,6 +166,59 @@ def port_sample(wl, hole, board, npl, n_queries):
                           int(npl[i % len(npl)]), wl["trials"], 1 + i)
     dt = time.perf_counter() - t0
     return n_queries * wl["trials"] * wl["players"] / dt, dt
+
+
+def cpu_baselines(wl, hole, board, npl, budget_cpp=12.0):
+    """the reference's C++ sibling, its Python run_montecarlo (1-s cut-off disabled), get_equity as shipped
+    (cut-off active) and the numpy2 sibling (results wrong post-flop upstream: timed, flagged), each on one core and
+    fanned out over all host cores, on queries of the workload.  Bounded to about 30 s of wall clock."""
+    import oracle
+    cores = host_cores()
+    Q, T, P = len(hole), wl["trials"], wl["players"]
+    out = {}
+    if oracle.ref_available():
+        v1, dt1 = reference_sample(wl, hole, board, npl, 1, 1)
+        n = min(max(1, Q), 2 * cores)
+        v, dt = reference_sample(wl, hole, board, npl, n, cores)
+        n = int(max(n, min(Q if Q > 1 else 64, n * budget_cpp / max(dt, 1e-3))))
+        v, dt = reference_sample(wl, hole, board, npl, n, cores)
+        out = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "%d queries x %d trials through the reference C++ montecarlo() (oracle/_ref), %d threads, %.1f s"
+                         % (n, T, cores, dt),
+               "cpp": {"one_core": v1, "all_cores": v, "cores": cores, "unit": UNIT,
+                       "sample": "1 query / %d queries x %d trials, Montecarlo.cpp:240-259 compiled in place" % (n, T)}}
+    else:
+        v, dt = port_sample(wl, hole, board, npl, 2)
+        out = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "2 queries x %d trials through oracle/npk_oracle.c, %.1f s" % (T, dt)}
+    try:
+        from oracle import ref_python
+        if not ref_python.available():
+            raise RuntimeError("baseline/_ref not built")
+        q0 = (hole[0], board[0], int(npl[0]))
+        eq, dt, ran = ref_python.python_run_montecarlo(*q0, T)
+        py1 = ran * P / dt
+        eqs, dts, rans = ref_python.python_get_equity_as_shipped(*q0, T)
+        procs = min(cores, 32)
+        qs = [(hole[i % Q], board[i % Q], int(npl[i % Q])) for i in range(procs)]
+        res, wall = ref_python.fan_out("python", qs, T, procs)
+        pyn = sum(r[2] for r in res) * P / wall
+        eq2, dt2, ran2 = ref_python.numpy2_montecarlo(*q0, T)
+        res2, wall2 = ref_python.fan_out("numpy2", qs * 4, T, procs)
+        out["python"] = {"one_core": py1, "all_cores": pyn, "processes": procs, "unit": UNIT,
+                         "sample": "MonteCarlo.run_montecarlo (montecarlo_python.py:191-252), timeout=+inf: 1 query x %d "
+                                   "trials in %.2f s (equity %.3f); %d processes x 1 query in %.2f s" % (T, dt, eq, procs, wall),
+                         "get_equity_as_shipped": {"seconds_per_call": dts, "trials_requested": T, "trials_run": rans,
+                                                   "calls_per_s_per_core": 1.0 / dts, "equity": eqs,
+                                                   "note": "montecarlo_python.py:401-406 stops after 1 s of wall clock"}}
+        out["numpy2"] = {"one_core": ran2 * P / dt2, "all_cores": sum(r[2] for r in res2) * P / wall2, "processes": procs,
+                         "unit": UNIT, "incorrect_results": True,
+                         "sample": "numpy_montecarlo (montecarlo_numpy2.py:333-346): 1 query x %d trials in %.2f s, equity "
+                                   "%.3f (wrong post-flop upstream, all its tests are skipped); %d processes x 4 queries in "
+                                   "%.2f s" % (T, dt2, eq2, procs, wall2)}
+    except Exception as exc:                                     # the GPU line must not die on a host-side baseline
+        out["python"] = {"unavailable": repr(exc)[:200]}
+    return out
 
 
 def run_reference_arm(args, wl, rank):
@@ -195,13 +257,57 @@ def run_reference_arm(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
-def run_exact(args, wl, rank, world, local_rank, dev):
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU legs.  Every leg returns a dict; all ranks run it, timings are the max over ranks.
+# ---------------------------------------------------------------------------------------------------------------------
+class Ctx(object):
+    def __init__(self, rank, world, local_rank, dev, L):
+        self.rank, self.world, self.local_rank, self.dev, self.L = rank, world, local_rank, dev, L
+
+    def max_over_ranks(self, x):
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor(x if isinstance(x, (list, tuple)) else [x], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = [float(a) for a in t.tolist()]
+        return v if isinstance(x, (list, tuple)) else v[0]
+
+    def sum_over_ranks(self, t):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+
+
+def int_issue_peak(L):
+    """Integer-issue peak of this GPU, measured in this run (roofline denominator)."""
+    import ctypes
+    from neuron_poker_b200 import _lib
+    peak, detail = 0.0, {}
+    for variant, nm in ((0, "lop3"), (1, "imad"), (2, "imad+lop3")):
+        v = ctypes.c_double(0)
+        ms = ctypes.c_float(0)
+        _lib.check(L.npk_int_peak(variant, 2000, ctypes.byref(v), ctypes.byref(ms)))
+        detail[nm] = v.value / 1e12
+        peak = max(peak, v.value)
+    return peak, detail
+
+
+def run_exact(args, wl, cx, steps=None):
     """cfg2: the exact kernels.  K3 enumerates every opponent hand x board completion of 4,096 heads-up turn
     spots and 4,096 river spots (seed-0 synthetic: 2 hole + 4 / 5 board cards, distinct, uniform); K2 ranks 64 M random
     7-card hands (7 B in, 2 B out per hand).  value = showdown evals/s of the enumeration (two hands per matchup)."""
     import torch
-    import torch.distributed as dist
     import neuron_poker_b200 as npk
+    rank, world, dev = cx.rank, cx.world, cx.dev
     Q = wl["queries"]
     g = torch.Generator().manual_seed(rank)
     cards = torch.rand(2 * Q, 52, generator=g).argsort(1)[:, :7].to(torch.uint8)
@@ -218,11 +324,10 @@ def run_exact(args, wl, rank, world, local_rank, dev):
         r = npk.rank7(hands)
     torch.cuda.synchronize()
     assert int((w + t + l).sum().item()) == matchups
-    if world > 1:
-        dist.barrier()
-    steps = min(args.steps, 50)
+    cx.barrier()
+    steps = min(args.steps, 50) if steps is None else steps
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(cx.local_rank)
     sampler.start()
     ev[0].record()
     for _ in range(steps):
@@ -233,10 +338,7 @@ def run_exact(args, wl, rank, world, local_rank, dev):
     ev[2].record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    enum_ms, rank_ms = (float(x) / steps for x in ms.tolist())
+    enum_ms, rank_ms = (x / steps for x in cx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]))
     # end to end: host arrays in, host arrays out
     hole_h, board_h, npl_h = hole.cpu().numpy(), board.cpu().numpy(), npl.cpu().numpy()
     t0 = time.perf_counter()
@@ -244,6 +346,7 @@ def run_exact(args, wl, rank, world, local_rank, dev):
         w, t, l = npk.enumerate_equity(hole_h, board_h, npl_h)
         w.cpu(); t.cpu(); l.cpu()
     e2e_s = (time.perf_counter() - t0) / 3
+    del hands
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -252,7 +355,7 @@ def run_exact(args, wl, rank, world, local_rank, dev):
         pass
     hbm = float(peaks.get("hbm_gbs", 6544.3))
     rank_gbs = n_hands * 9 / (rank_ms * 1e-3) / 1e9
-    line = {"metric": METRIC, "value": 2 * matchups * world / (enum_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+    return {"metric": METRIC, "value": 2 * matchups * world / (enum_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(3, args.warmup), "ms_per_step": enum_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "spots_per_gpu": 2 * Q, "matchups_per_step": matchups,
@@ -265,17 +368,16 @@ def run_exact(args, wl, rank, world, local_rank, dev):
             "roofline": {"bound": "hbm", "kernel": "rank7_kernel", "achieved": rank_gbs, "peak": hbm, "unit": "GB/s",
                          "frac": rank_gbs / hbm, "traffic": None,
                          "algorithmic_bytes_per_hand": 9, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6544.3"}}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
 
 
-def run_selfplay(args, wl, rank, world, local_rank, dev, L):
+def run_selfplay(args, wl, cx, deal, steps=None):
     """cfg5: every rank owns 65,536 six-max tables (4 equity agents + 2 random ones, main.py:136-150).  One step = one
     action on every table: equity query of the current player (1,000 runs, all players alive, env.py:262-264) -> Monte-Carlo
     kernels -> agent decisions -> betting state machine -> finished games restarted; nothing leaves the device."""
     import torch
-    import torch.distributed as dist
     from neuron_poker_b200.holdem import EquityAgents, HoldemTables
+    rank, world, dev = cx.rank, cx.world, cx.dev
+    steps = args.steps if steps is None else steps
     N, runs = wl["queries"], wl["trials"]
     tb = HoldemTables(N, n_players=6, seed=7, table_offset=rank * N, autoplay=[1] * 6, device=dev)
     agents = EquityAgents.equity_vs_random()
@@ -283,7 +385,7 @@ def run_selfplay(args, wl, rank, world, local_rank, dev, L):
     acted = torch.zeros((), dtype=torch.int64, device=dev)
 
     def step(count):
-        tb.selfplay_step(agents, runs=runs, deal_mode=args.deal)
+        tb.selfplay_step(agents, runs=runs, deal_mode=deal)
         if count:
             _, _, npl, active = tb._q
             evals.add_((npl.to(torch.int64) * active.to(torch.int64)).sum() * runs)
@@ -291,39 +393,33 @@ def run_selfplay(args, wl, rank, world, local_rank, dev, L):
 
     for _ in range(max(args.warmup, 30)):           # reach a steady mix of streets and player counts
         step(False)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
+    cx.barrier()
+    sampler = ClockSampler(cx.local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(True)
     e1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    dev_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    tot = torch.stack([evals, acted]).to(torch.float64)
-    if world > 1:
-        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot)
-    dev_ms = float(dev_ms.item())
+    dev_ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    tot = cx.sum_over_ranks(torch.stack([evals, acted]).to(torch.float64))
     st = tb.state()
-    # end to end: the same loop with the actions and rewards of every step copied to the host
+    # end to end: the same loop with the rewards of every step copied to the host
     w0 = time.perf_counter()
-    n_e2e = max(3, min(args.steps, 50))
+    n_e2e = max(3, min(steps, 50))
     ev0 = int(evals.item())
     for _ in range(n_e2e):
         step(True)
         tb.rewards.cpu()
-    e2e_s = time.perf_counter() - w0
+    e2e_s = cx.max_over_ranks(time.perf_counter() - w0)
     e2e_evals = (int(evals.item()) - ev0) * world
-    line = {
-        "metric": METRIC, "value": float(tot[0].item()) / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 30), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    return {
+        "metric": METRIC, "value": float(tot[0].item()) / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": max(args.warmup, 30), "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": wl["name"], "tables_per_gpu": N, "runs_per_action": runs, "deal_mode": args.deal,
+        "config": {"workload": wl["name"], "tables_per_gpu": N, "runs_per_action": runs, "deal_mode": deal,
                    "agents": "4 x agent_consider_equity + 2 x agent_random (main.py:136-150)",
                    "table_actions_per_s": float(tot[1].item()) / (dev_ms * 1e-3),
                    "mean_players_per_query": float(tot[0].item()) / max(1.0, float(tot[1].item()) * runs),
@@ -332,56 +428,95 @@ def run_selfplay(args, wl, rank, world, local_rank, dev, L):
         "clocks": clocks,
         "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * N,
                 "steps": n_e2e, "api": "HoldemTables.selfplay_step + rewards.cpu()"},
-        "gpu_launches": args.steps * (6 if args.deal == "reference" else 26),
+        "gpu_launches": steps * tb.launches_per_step if hasattr(tb, "launches_per_step") else None,
     }
-    if rank == 0:
-        print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3")
-    ap.add_argument("--deal", default="uniform", choices=["uniform", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    wl = workload(args.workload)
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference_arm(args, wl, rank)
-        return
-
-    import numpy as np
+def run_ranges(args, wl, cx, steps=None):
+    """Opponent ranges (montecarlo_python.py:136-181): 4,096 six-player flop queries x 1,000 trials, every
+    opponent restricted to the top 30 % of the reference's preflop ranking, reference dealer (equity_ranges_kernel<1>)."""
     import torch
-    import torch.distributed as dist
     import neuron_poker_b200 as npk
-    from neuron_poker_b200 import _lib
-    import ctypes
+    dev = cx.dev
+    steps = min(args.steps, 20) if steps is None else steps
+    hole_h, board_h, npl_h = make_queries(wl, cx.world, cx.rank)
+    hole, board, npl = (torch.as_tensor(x).to(dev) for x in (hole_h, board_h, npl_h))
+    Q, T, P = len(hole_h), wl["trials"], wl["players"]
+    out = {"wins": torch.zeros(Q, dtype=torch.int64, device=dev), "ties": torch.zeros(Q, dtype=torch.int64, device=dev),
+           "passes": torch.zeros(Q, dtype=torch.int64, device=dev)}
 
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    os.environ["NPK_DEVICE"] = str(local_rank)
-    dev = torch.device("cuda", local_rank)
-    L = _lib.ensure_init(local_rank)
+    def step(i):
+        for v in out.values():
+            if isinstance(v, torch.Tensor):
+                v.zero_()
+        npk.get_equity_ranges_batch(hole, board, npl, T, opponent_range=0.3, seed_value=300 + i, deal_mode=args.deal_ranges,
+                                    query_offset=cx.rank * Q, validate=False, passes=True, out=out)
 
-    if args.workload == "cfg2":
-        run_exact(args, wl, rank, world, local_rank, dev)
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    if args.workload == "cfg5":
-        run_selfplay(args, wl, rank, world, local_rank, dev, L)
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    for i in range(3):
+        step(i)
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    attempts = float(out["passes"].double().sum().item()) / (Q * T * (P - 1))
+    return {"metric": METRIC, "value": Q * T * P * cx.world / (ms * 1e-3), "unit": UNIT, "n_gpus": cx.world, "steps": steps,
+            "ms_per_step": ms, "scaling": "weak", "dtype": "u32", "data": "synthetic",
+            "config": {"workload": wl["name"], "queries_per_gpu": Q, "trials": T, "players": P, "opponent_range": 0.3,
+                       "deal_mode": args.deal_ranges, "attempts_per_opponent_hand": attempts,
+                       "mean_equity": float((out["wins"] + out["ties"]).double().mean().item() / T)},
+            "gpu_launches": steps, "kernel": "equity_ranges_kernel<%d>" % (1 if args.deal_ranges == "reference" else 0)}
 
+
+def run_latency(args, wl, cx, with_cpu):
+    """cfg1 (BASELINE config 1): get_equity({'AS','KS'}, set(), 2, 10000) -- one blocking call from Python, string parsing,
+    launch, synchronisation and result read-back inside.  GPU through the drop-in; CPU through the reference's own
+    tools/montecarlo_python.get_equity (as shipped, 1-s cut-off) and run_montecarlo without the cut-off."""
+    import neuron_poker_b200 as npk
+    res = {"workload": wl["name"]}
+    for name, fn in (("get_equity", lambda: npk.get_equity({"AS", "KS"}, set(), 2, 10000)),
+                     ("montecarlo", lambda: npk.montecarlo({"AS", "KS"}, {"null"}, 2, 10000))):
+        for _ in range(30):
+            fn()
+        n = 400
+        t0 = time.perf_counter()
+        vals = [fn() for _ in range(n)]
+        dt = time.perf_counter() - t0
+        res[name] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt, "mean_equity": sum(vals) / n, "calls": n,
+                     "dealer": "reference (montecarlo_python.py:165-189)" if name == "get_equity" else "uniform (Montecarlo.cpp:293-312)"}
+    # the other half of BASELINE.json's metric: get_equity calls/s at 10,000 trials, 6 players
+    fn = lambda: npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)      # noqa: E731
+    for _ in range(30):
+        fn()
+    n = 400
+    t0 = time.perf_counter()
+    vals = [fn() for _ in range(n)]
+    dt = time.perf_counter() - t0
+    res["get_equity_6_players_flop"] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt, "mean_equity": sum(vals) / n}
+    if with_cpu:
+        try:
+            from oracle import ref_python
+            h, b = [51, 47], [255] * 5
+            eq, dt, ran = ref_python.python_get_equity_as_shipped(h, b, 2, 10000)
+            eq2, dt2, ran2 = ref_python.python_run_montecarlo(h, b, 2, 10000)
+            res["cpu_reference"] = {"get_equity_as_shipped": {"seconds": dt, "trials_run": ran, "equity": eq},
+                                    "run_montecarlo_no_cutoff": {"seconds": dt2, "trials_run": ran2, "equity": eq2},
+                                    "cores": 1, "source": "baseline/_ref/tools/montecarlo_python.py (unmodified copy)"}
+            res["speedup_vs_python_full_10k"] = dt2 / (res["get_equity"]["us_per_call"] * 1e-6)
+        except Exception as exc:
+            res["cpu_reference"] = {"unavailable": repr(exc)[:200]}
+    return res
+
+
+def run_mc(args, wl, cx, deal, steps, warmup, peak=None, peak_detail=None, e2e=True, flush=True):
+    """The Monte-Carlo kernels on a uniform-shape batch: cfg3 (query blocks per rank, no collective) and cfg4 (trial ranges
+    per rank, the [2,Q] count all-reduce inside the timed step)."""
+    import torch
+    import neuron_poker_b200 as npk
+    rank, world, dev = cx.rank, cx.world, cx.dev
     hole_h, board_h, npl_h = make_queries(wl, world, rank)
     Q, T, P, B = len(hole_h), wl["trials"], wl["players"], wl["known"]
     hole, board, npl = (torch.as_tensor(x).to(dev) for x in (hole_h, board_h, npl_h))
@@ -390,158 +525,248 @@ def main():
     q_off = 0 if wl["shard"] == "trial" else rank * Q
     both = torch.zeros((2, Q), dtype=torch.int64, device=dev)              # wins row, ties row: one tensor to all-reduce
     out = {"wins": both[0], "ties": both[1]}
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-
-    # integer-issue peak of this GPU, measured in this run (roofline denominator)
-    peak = 0.0
-    peak_detail = {}
-    for variant, nm in ((0, "lop3"), (1, "imad"), (2, "imad+lop3")):
-        v = ctypes.c_double(0)
-        ms = ctypes.c_float(0)
-        _lib.check(L.npk_int_peak(variant, 2000, ctypes.byref(v), ctypes.byref(ms)))
-        peak_detail[nm] = v.value / 1e12
-        peak = max(peak, v.value)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush else None      # > 126 MB L2
+    job = npk.dist.TrialShardedJob(hole, board, npl, (P, B), rank, world, deal_mode=deal) if by_trial else None
 
     def step(i):
         if by_trial:
-            # the kernel accumulates into the two rows of one [2,Q] tensor; a single all-reduce combines the ranks'
-            # trial ranges
-            both.zero_()
-            npk.get_equity_batch(hole, board, npl, t_cnt, seed_value=1000 + i, deal_mode=args.deal, trial_offset=t_off,
-                                 uniform_shape=(P, B), validate=False, out=out)
-            npk.dist.allreduce_counts(both)
-        else:
-            both.zero_()
-            npk.get_equity_batch(hole, board, npl, T, seed_value=1000 + i, deal_mode=args.deal, query_offset=q_off,
-                                 uniform_shape=(P, B), validate=False, out=out)
+            return job.step(T, 1000 + i)                 # kernel on this rank's trial range + the count reduction
+        both.zero_()
+        npk.get_equity_batch(hole, board, npl, T, seed_value=1000 + i, deal_mode=deal, query_offset=q_off,
+                             uniform_shape=(P, B), validate=False, out=out)
+        return both
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
+    cx.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    sampler = ClockSampler(cx.local_rank)
     sampler.start()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush_buf.fill_(i & 0xFF)                      # evict L2 between timed steps (outside the events)
+    res = both
+    for i in range(steps):
+        if flush:
+            flush_buf.fill_(i & 0xFF)                      # evict L2 between timed steps (outside the events)
         starts[i].record()
-        step(args.warmup + i)
+        res = step(warmup + i)
         ends[i].record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    if world > 1:
-        dist.barrier()
-    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    check_eq = float((out["wins"] + out["ties"]).double().mean().item() / (T if not by_trial else T)) if not by_trial \
-        else float((both[0] + both[1]).double().mean().item() / T)
-
+    cx.barrier()
+    dev_ms = cx.max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)))
+    check_eq = float((res[0] + res[1]).double().mean().item() / T)
     evals_per_step = Q * T * P * (1 if by_trial else world)      # whole job, all ranks
-    value = evals_per_step * args.steps / (dev_ms * 1e-3)
-
-    # end to end through the host-buffer API: queries in host memory, counters back in host memory, every step
-    e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5000 + i, deal_mode=args.deal)
-    if world > 1:
-        dist.barrier()
-    pinned = [torch.as_tensor(x).pin_memory() for x in (hole_h, board_h, npl_h)]
-    e0 = time.perf_counter()
-    for i in range(e2e_steps):
-        if by_trial:
-            # a trial shard of a larger job: host queries -> device, this rank's trial range, NCCL all-reduce of the
-            # counters, totals back to the host (the host-buffer C entry point has no trial offset)
-            h, b_, n_ = (x.to(dev, non_blocking=True) for x in pinned)
-            both.zero_()
-            npk.get_equity_batch(h, b_, n_, t_cnt, seed_value=6000 + i, deal_mode=args.deal, trial_offset=t_off,
-                                 uniform_shape=(P, B), validate=False, out=out)
-            npk.dist.allreduce_counts(both)
-            r = both.cpu()
-        else:
-            r = npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=args.deal)
-    e2e_s = time.perf_counter() - e0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = Q * t_cnt * P * world * e2e_steps / e2e_s
-
-    # the other half of BASELINE.json's metric: blocking get_equity calls per second at 10,000 trials, 6 players
-    # (string parsing, H2D, launch, sync and D2H all inside; reference dealer, like the reference's own get_equity)
-    calls = None
-    if rank == 0:
-        for _ in range(20):
-            npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
-        n_calls = 300
-        c0 = time.perf_counter()
-        for _ in range(n_calls):
-            npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
-        calls = n_calls / (time.perf_counter() - c0)
-
-    kernel_name = "equity_uniform_kernel<%d,%d>" % (P - 1, 5 - B) if args.deal == "uniform" else "equity_refdeal_kernel<%d,%d>" % (P - 1, 5 - B)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t_rec = json.load(f).get(kernel_name)
-        if t_rec and wl["name"].startswith("cfg3"):
-            traffic = t_rec["dram_bytes_read"] + t_rec["dram_bytes_write"]
-    except Exception:
-        pass
-
+    value = evals_per_step * steps / (dev_ms * 1e-3)
+    kernel_ms = dev_ms / steps
     a_instr = algorithmic_instr(P, B)
-    kernel_ms = dev_ms / args.steps
-    achieved = Q * t_cnt * a_instr / (kernel_ms * 1e-3)          # per GPU
+    kname = ("equity_uniform_kernel<%d,%d>" if deal == "uniform" else "equity_refdeal_kernel<%d,%d>") % (P - 1, 5 - B)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if by_trial else "weak",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if wl["shard"] == "trial" else "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": wl["name"], "queries_per_gpu": Q, "trials": T, "players": P, "known_board_cards": B,
-                   "deal_mode": args.deal, "sharding": ("trial ranges + NCCL all-reduce of [2,Q] counters" if by_trial
-                                                        else "query blocks, no collective"),
-                   "l2": "flushed (256 MiB fill) between timed steps; inputs are 28 KB", "mean_equity": check_eq,
-                   "wall_s_timed_loop": wall},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(8 * Q), "d2h_bytes_per_step": int(16 * Q),
-                "steps": e2e_steps,
-                "api": ("pinned host queries -> get_equity_batch(trial shard) -> NCCL all-reduce -> host" if by_trial
-                        else "neuron_poker_b200.equity_counts_batch -> npk_equity_host")},
-        "gpu_launches": args.steps,
-        "get_equity_calls_per_s": calls,
-        "roofline": {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tthread-instr/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json); "
-                                     "the kernel is bound by integer issue and shared memory, not HBM",
-                     "kernel": kernel_name,
-                     "algorithmic_instr_per_trial": a_instr, "peak_source": "npk_int_peak measured in this run",
-                     "peak_variants": peak_detail, "nominal_issue_peak": 148 * 128 * 1.965e9 / 1e12},
+                   "deal_mode": deal, "sharding": ((job.describe() if by_trial else "one rank: the whole trial range")
+                                                   if wl["shard"] == "trial" else "query blocks, no collective"),
+                   "l2": ("flushed (256 MiB fill) between timed steps; " if flush else "not flushed; ") + "inputs are %d B" % (8 * Q),
+                   "mean_equity": check_eq, "wall_s_timed_loop": wall,
+                   "device_timed_call": "get_equity_batch(uniform_shape=(P,B), validate=False): query validation and shape "
+                                        "classification are skipped in `value`; the e2e leg validates every query on the host"},
+        "clocks": clocks, "gpu_launches": steps * (job.launches_per_step if by_trial else 1),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle
-        cores = host_cores()
-        if oracle.ref_available():
-            n = min(max(1, Q), 2 * cores)
-            v, dt = reference_sample(wl, hole_h, board_h, npl_h, n, cores)
-            n = int(max(n, min(Q if Q > 1 else 64, n * 12.0 / max(dt, 1e-3))))      # about 12 s of host work
-            v, dt = reference_sample(wl, hole_h, board_h, npl_h, n, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                                    "sample": "%d queries x %d trials through the reference C++ montecarlo() "
-                                              "(oracle/_ref), %d threads, %.1f s" % (n, T, cores, dt)}
-        else:
-            v, dt = port_sample(wl, hole_h, board_h, npl_h, 2)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "2 queries x %d trials through oracle/npk_oracle.c, %.1f s" % (T, dt)}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+    if peak:
+        achieved = Q * t_cnt * a_instr / (kernel_ms * 1e-3)          # per GPU
+        line["roofline"] = {"bound": "int_issue", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tthread-instr/s",
+                            "frac": achieved / peak, "traffic": None, "kernel": kname, "algorithmic_instr_per_trial": a_instr,
+                            "peak_source": "npk_int_peak measured in this run", "peak_variants": peak_detail,
+                            "nominal_issue_peak": 148 * 128 * 1.965e9 / 1e12}
+    if e2e:
+        # end to end through the host-buffer API: queries in host memory, counters back in host memory, every step
+        e2e_steps = max(3, min(steps, 20))
+        for i in range(2):
+            npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5000 + i, deal_mode=deal)
+        cx.barrier()
+        pinned = [torch.as_tensor(x).pin_memory() for x in (hole_h, board_h, npl_h)]
+        e0 = time.perf_counter()
+        for i in range(e2e_steps):
+            if by_trial:
+                # a trial shard of a larger job: host queries -> device, this rank's trial range, the count reduction,
+                # totals back to the host (the host-buffer C entry point has no trial offset)
+                job.load(*(x.to(dev, non_blocking=True) for x in pinned))
+                r = job.step(T, 6000 + i).cpu()
+            else:
+                r = npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=deal)
+        e2e_s = cx.max_over_ranks(time.perf_counter() - e0)
+        line["e2e"] = {"value": Q * t_cnt * P * world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(8 * Q),
+                       "d2h_bytes_per_step": int(16 * Q), "steps": e2e_steps,
+                       "api": ("pinned host queries -> TrialShardedJob.step (trial shard + count reduction) -> host" if by_trial
+                               else "neuron_poker_b200.equity_counts_batch -> npk_equity_host")}
+    return line, (hole_h, board_h, npl_h)
+
+
+def run_strong(args, cx, deal="uniform", steps=10):
+    """cfg4 at this world size: strong scaling.  Times (a) the trial-sharded step with the count reduction inside,
+    (b) the unsharded job on one GPU (every rank runs it, nothing is exchanged), and asserts on the device that the reduced
+    counters of the sharded run equal the unsharded ones bit for bit for the same seed."""
+    import torch
+    import neuron_poker_b200 as npk
+    wl = workload("cfg4")
+    sharded, _ = run_mc(args, wl, cx, deal, steps, 3, e2e=False, flush=False)
+    one = Ctx(0, 1, cx.local_rank, cx.dev, cx.L)                # the same job, whole trial range, this GPU alone
+    alone, _ = run_mc(args, wl, one, deal, max(3, steps // 2), 2, e2e=False, flush=False)
+    t1 = cx.max_over_ranks(alone["ms_per_step"])
+    hole_h, board_h, npl_h = make_queries(wl, 1, 0)
+    hole, board, npl = (torch.as_tensor(x).to(cx.dev) for x in (hole_h, board_h, npl_h))
+    T, P, B = wl["trials"] // 10, wl["players"], wl["known"]
+    ref = npk.get_equity_batch(hole, board, npl, T, seed_value=77, deal_mode=deal, uniform_shape=(P, B), validate=False)
+    job = npk.dist.TrialShardedJob(hole, board, npl, (P, B), cx.rank, cx.world, deal_mode=deal)
+    got = job.step(T, 77)
+    same = bool(torch.equal(got[0], ref["wins"]) and torch.equal(got[1], ref["ties"]))
+    same = cx.max_over_ranks(0.0 if same else 1.0) == 0.0
+    assert same, "trial-sharded counters differ from the unsharded run"
+    sharded["strong_scaling"] = {"ms_per_step_one_gpu_unsharded": t1, "ms_per_step_sharded": sharded["ms_per_step"],
+                                 "efficiency": t1 / (cx.world * sharded["ms_per_step"]), "n_gpus": cx.world,
+                                 "sharded_equals_unsharded_bit_exact": same,
+                                 "check": "169 classes x %d trials, seed 77: reduced [2,169] counters of the %d-way trial "
+                                          "split == one-GPU counters (torch.equal on the device, all ranks)" % (T, cx.world),
+                                 "reduction": job.describe()}
+    return sharded
+
+
+def run_sustained(args, cx, deal="uniform", seconds=3.0):
+    """The cfg3 step launched back to back for >= `seconds` of device time (no L2 flush, no host synchronisation inside):
+    what the part sustains once power and thermals have settled, with its own clock samples."""
+    import torch
+    import neuron_poker_b200 as npk
+    wl = workload("cfg3")
+    hole_h, board_h, npl_h = make_queries(wl, cx.world, cx.rank)
+    Q, T, P, B = len(hole_h), wl["trials"], wl["players"], wl["known"]
+    hole, board, npl = (torch.as_tensor(x).to(cx.dev) for x in (hole_h, board_h, npl_h))
+    both = torch.zeros((2, Q), dtype=torch.int64, device=cx.dev)
+    out = {"wins": both[0], "ties": both[1]}
+
+    def step(i):
+        npk.get_equity_batch(hole, board, npl, T, seed_value=9000 + i, deal_mode=deal, query_offset=cx.rank * Q,
+                             uniform_shape=(P, B), validate=False, out=out)
+
+    for i in range(5):
+        step(i)
+    cx.barrier()
+    n = int(seconds / 0.5e-3 * 1.15)
+    sampler = ClockSampler(cx.local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    total = int(both.sum().item())
+    assert 0 < total <= (5 + n) * Q * T
+    return {"value": Q * T * P * cx.world * n / (ms * 1e-3), "unit": UNIT, "steps": n, "seconds": ms * 1e-3,
+            "ms_per_step": ms / n, "clocks": clocks, "deal_mode": deal,
+            "note": "back-to-back launches of the cfg3 step, counters accumulate (no reset, no L2 flush: the step reads 28 KB "
+                    "of queries and 131 KB of tables per CTA)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="all")
+    ap.add_argument("--deal", default="uniform", choices=["uniform", "reference"])
+    ap.add_argument("--deal-ranges", dest="deal_ranges", default="reference", choices=["uniform", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="cfg3 headline only (profiling runs)")
+    args = ap.parse_args()
+    everything = args.workload == "all"
+    wl = workload("cfg3" if everything else args.workload)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, wl, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from neuron_poker_b200 import _lib
+
     if world > 1:
-        dist.destroy_process_group()
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    os.environ["NPK_DEVICE"] = str(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = _lib.ensure_init(local_rank)
+    cx = Ctx(rank, world, local_rank, dev, L)
+    with_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+
+    def finish(line):
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+
+    if args.workload == "cfg2":
+        return finish(run_exact(args, wl, cx))
+    if args.workload == "cfg5":
+        return finish(run_selfplay(args, wl, cx, args.deal))
+    if args.workload == "ranges":
+        return finish(run_ranges(args, wl, cx))
+    if args.workload == "cfg1":
+        return finish({"metric": "get_equity_latency", "config": {"workload": wl["name"]}, **run_latency(args, wl, cx, with_cpu)})
+    if args.workload == "cfg4":
+        line = run_strong(args, cx, args.deal, steps=min(args.steps, 50))
+        return finish(line)
+
+    peak, peak_detail = int_issue_peak(L)
+    line, (hole_h, board_h, npl_h) = run_mc(args, wl, cx, args.deal, args.steps, max(3, args.warmup), peak, peak_detail)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t_rec = json.load(f).get(line["roofline"]["kernel"])
+        if t_rec:
+            line["roofline"]["traffic"] = t_rec["dram_bytes_read"] + t_rec["dram_bytes_write"]
+            line["roofline"]["traffic_note"] = ("DRAM bytes per launch from the committed ncu --set full capture "
+                                                "(profiles/ncu_traffic.json); the kernel is bound by integer issue and shared "
+                                                "memory, not HBM")
+    except Exception:
+        pass
+    if not (everything and not args.no_extras):
+        if with_cpu:
+            line["cpu_baseline"] = cpu_baselines(wl, hole_h, board_h, npl_h)
+        return finish(line)
+
+    # ---- everything else BASELINE.json names, in the same run -------------------------------------------------------
+    line["sustained"] = run_sustained(args, cx, args.deal)
+    extras = {}
+    lat = run_latency(args, workload("cfg1"), cx, with_cpu) if rank == 0 else None
+    line["get_equity_calls_per_s"] = lat["get_equity_6_players_flop"]["calls_per_s"] if lat else None
+    extras["cfg1"] = lat
+    cx.barrier()
+
+    def brief(rec, keep=("value", "unit", "ms_per_step", "steps", "scaling", "config", "roofline", "e2e", "strong_scaling",
+                         "gpu_launches", "clocks", "kernel")):
+        return {k: rec[k] for k in keep if k in rec}
+
+    extras["cfg2"] = brief(run_exact(args, workload("cfg2"), cx, steps=10))
+    ref3, _ = run_mc(args, workload("cfg3"), cx, "reference", 20, 3, peak, peak_detail, e2e=False)
+    extras["cfg3_reference_dealer"] = brief(ref3)
+    extras["cfg4"] = brief(run_strong(args, cx, "uniform", steps=10))
+    extras["cfg4_reference_dealer"] = brief(run_strong(args, cx, "reference", steps=4))
+    extras["cfg5_uniform"] = brief(run_selfplay(args, workload("cfg5"), cx, "uniform", steps=30))
+    extras["cfg5_reference_dealer"] = brief(run_selfplay(args, workload("cfg5"), cx, "reference", steps=30))
+    extras["ranges"] = brief(run_ranges(args, workload("ranges"), cx, steps=5))
+    line["workloads"] = extras
+    if with_cpu:
+        line["cpu_baseline"] = cpu_baselines(wl, hole_h, board_h, npl_h)
+    finish(line)
 
 
 if __name__ == "__main__":

@@ -108,6 +108,29 @@ int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint
                            uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
                            void* stream);
 
+/*
+ * Trial-sharded jobs (one query spans several GPUs, e.g. 169 classes x 1,000,000 trials over 8 GPUs): the
+ * count reduction is done by the Monte-Carlo kernel itself over NVLink-mapped peer memory; no NCCL call, no memset and no
+ * pack kernel on the step path.  One process per GPU; the processes exchange 64-byte CUDA IPC handles once (any transport:
+ * the Python host side uses torch.distributed.all_gather):
+ *   npk_peer_create   allocates this rank's exchange buffer (2 parities x world slots x max_words u64) on the current
+ *                     device and returns its IPC handle in handle[64] (HOST)
+ *   npk_peer_connect  handles = all ranks' handles in rank order (HOST, world x 64 bytes): maps every peer's buffer
+ *   npk_equity_batch_sharded  runs THIS rank's share of `trials_total` trials (rank r takes the r-th contiguous range) of
+ *                     a uniform-shape batch and leaves in totals[2*Q] (device; wins [Q] then ties [Q]) the counters summed
+ *                     over all ranks: the last warp of each rank's grid pushes the rank's counters into its slot on every
+ *                     rank, publishes an epoch, waits for every rank's epoch and sums.  Every rank must make the same
+ *                     sequence of calls; totals are bit-identical to the unsharded job.  Asynchronous on `stream`.
+ *   npk_peer_error    HOST, synchronises: 1 if a peer's counters did not arrive within ~2 s in an earlier step
+ */
+int npk_peer_create(int rank, int world, int64_t max_words, void** group, uint8_t* handle);
+int npk_peer_connect(void* group, const uint8_t* handles);
+int npk_peer_destroy(void* group);
+int npk_peer_error(void* group, int* error);
+int npk_equity_batch_sharded(void* group, const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q,
+                             int64_t trials_total, int players, int known, uint64_t seed, int64_t query_offset,
+                             int deal_mode, uint64_t* totals, void* stream);
+
 /* HOST buffers in, HOST buffers out: copies the queries to the device (pinned staging owned by the library), runs
  * npk_equity_batch with validation, copies the counters back and returns when they are valid.  wins/ties (and the
  * optional win_types [Q,9], passes [Q]) are overwritten. */

@@ -53,6 +53,11 @@ def lib():
                                                       ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
                 L.npk_equity_ranges_host.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i32, u64, u64,
                                                      u64, u64]
+                L.npk_peer_create.argtypes = [i32, i32, i64, ctypes.POINTER(ctypes.c_void_p), vp]
+                L.npk_peer_connect.argtypes = [vp, vp]
+                L.npk_peer_destroy.argtypes = [vp]
+                L.npk_peer_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int)]
+                L.npk_equity_batch_sharded.argtypes = [vp, u8, u8, u8, i64, i64, i32, i32, ctypes.c_uint64, i64, i32, u64, vp]
                 L.npk_rank7_batch.argtypes = [u8, i64, u16, vp]
                 L.npk_rank7_colex.argtypes = [i64, i64, u16, vp]
                 L.npk_enum_batch.argtypes = [u8, u8, u8, i64, u64, u64, u64, vp]

@@ -58,6 +58,26 @@ struct HostStage {
     cudaStream_t stream = nullptr;
 } g_stage;
 
+// Tuning aids, read from the environment ONCE (a getenv per launch costs as much as the launch of a 30 us call).
+struct Tuning {
+    long long chunk = 0;        // NPK_CHUNK: trials per work item
+    int warps = 0;              // NPK_WARPS: warps per CTA of the Monte-Carlo kernels
+    bool serial_groups = false; // NPK_SERIAL_GROUPS: mixed batches one shape after another instead of side by side
+    bool no_single_path = false;// NPK_NO_SINGLE_PATH: one-query host calls through the general path
+    Tuning()
+    {
+        if (const char* e = getenv("NPK_CHUNK")) chunk = atoll(e);
+        if (const char* e = getenv("NPK_WARPS")) warps = atoi(e);
+        serial_groups = getenv("NPK_SERIAL_GROUPS") != nullptr;
+        no_single_path = getenv("NPK_NO_SINGLE_PATH") != nullptr;
+    }
+};
+const Tuning& tuning()
+{
+    static const Tuning t;
+    return t;
+}
+
 int fail(int code, const std::string& msg)
 {
     g_err = msg;
@@ -179,7 +199,7 @@ uint32_t pick_chunk(long long queries, long long trials, int sm_count, int lanes
 {
     const long long warps = (long long)sm_count * 16;
     long long c = (queries * trials) / (8 * warps);
-    if (getenv("NPK_CHUNK")) c = atoll(getenv("NPK_CHUNK"));      // tuning aid
+    if (tuning().chunk > 0) c = tuning().chunk;
     c = (c + lanes_worth - 1) / lanes_worth * lanes_worth;      // a warp iteration covers 64 trials (a pair per lane)
     if (c < lanes_worth) c = lanes_worth;
     if (c > 2048) c = 2048;
@@ -380,7 +400,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
     p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
     p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);      // + 15 diagnostic words, all inside the header
 
-    const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;   // tuning aid
+    const int forced_warps = tuning().warps;
     if (uniform_shape) {
         p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
         e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p, Q * chunks, ds->sm_count, forced_warps, s);
@@ -408,7 +428,7 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         total_weight += weight[g];
         n_groups++;
     }
-    const bool side_by_side = n_groups > 1 && !getenv("NPK_SERIAL_GROUPS");
+    const bool side_by_side = n_groups > 1 && !tuning().serial_groups;
     if (side_by_side && !ds->streams_ready) {
         for (int g = 0; g < kGroupStreams; g++) {
             if ((e = cudaStreamCreateWithFlags(&ds->group_stream[g], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
@@ -482,7 +502,7 @@ int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint
     p.qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
     p.nq = 0;
     const long long chunks = (trials + p.chunk - 1) / p.chunk;
-    const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;
+    const int forced_warps = tuning().warps;
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
     const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
     for (int g = 0; g < kGroups; g++) {
@@ -509,7 +529,7 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lk(g_host_mu);
     cudaError_t e;
-    if (Q == 1 && !getenv("NPK_NO_SINGLE_PATH")) {
+    if (Q == 1 && !tuning().no_single_path) {
         // One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in
         // device memory between calls (the last warp hands them over and zeroes them), the result lands in mapped host
         // memory.  No H2D / D2H copy, no memset.
@@ -561,7 +581,7 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
         p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &ds->single->passes : nullptr;
         p.abort_flag = ds->single->abort_flag;
         const long long chunks = (trials + p.chunk - 1) / p.chunk;
-        const int forced_warps = getenv("NPK_WARPS") ? atoi(getenv("NPK_WARPS")) : 0;
+        const int forced_warps = tuning().warps;
         e = npk::launch_equity_uniform(n_players[0] - 1, 5 - known, p, chunks, ds->sm_count, forced_warps, ds->single_stream);
         if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
         if ((e = cudaStreamSynchronize(ds->single_stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
@@ -636,6 +656,146 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     if (passes) std::memcpy(passes, st.h_out + 11 * Q, 8 * Q);
     return NPK_OK;
 }
+
+// ---- trial-sharded jobs: count reduction over NVLink peer memory inside the kernel -----------------------------------------
+namespace {
+struct PeerGroup {
+    int device = -1, rank = 0, world = 1;
+    int64_t stride = 0;                       // u64 words per (parity, rank) slot
+    uint8_t* buf = nullptr;                   // this rank's PeerBuf: flags [2][kMaxPeers] u64, then slots [2][world][stride] u64
+    void* peer_buf[npk::kMaxPeers] = {};      // every rank's buffer in this process's address space (own: buf)
+    npk::PeerCall* call = nullptr;            // device copy of the pointers + local counters' bookkeeping
+    unsigned long long* acc = nullptr;        // local counters [stride]
+    uint32_t* abort_flag = nullptr;
+    unsigned long long epoch = 0;
+    bool connected = false;
+};
+constexpr size_t kPeerFlagBytes = 2 * npk::kMaxPeers * sizeof(unsigned long long);
+}  // namespace
+
+extern "C" {
+
+int npk_peer_create(int rank, int world, int64_t max_words, void** group, uint8_t* handle /*[64] host*/)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (!group || !handle || world < 1 || world > npk::kMaxPeers || rank < 0 || rank >= world || max_words < 2)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "npk_peer_create: 1..16 ranks, rank inside, max_words >= 2");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    PeerGroup* g = new PeerGroup;
+    cudaGetDevice(&g->device);
+    g->rank = rank; g->world = world; g->stride = max_words;
+    const size_t bytes = kPeerFlagBytes + (size_t)2 * world * max_words * 8;
+    cudaError_t e = cudaMalloc(&g->buf, bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->buf, 0, bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->acc, (size_t)max_words * 8);
+    if (e == cudaSuccess) e = cudaMemset(g->acc, 0, (size_t)max_words * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&g->call, sizeof(npk::PeerCall));
+    if (e == cudaSuccess) e = cudaMalloc(&g->abort_flag, 64);
+    if (e == cudaSuccess) e = cudaMemset(g->abort_flag, 0, 64);
+    cudaIpcMemHandle_t h;
+    std::memset(&h, 0, sizeof h);
+    if (e == cudaSuccess && world > 1) e = cudaIpcGetMemHandle(&h, g->buf);
+    if (e != cudaSuccess) {
+        cudaFree(g->buf); cudaFree(g->acc); cudaFree(g->call); cudaFree(g->abort_flag);
+        delete g;
+        return cuda_fail(e, "npk_peer_create");
+    }
+    std::memcpy(handle, &h, 64);
+    *group = g;
+    return NPK_OK;
+}
+
+int npk_peer_connect(void* group, const uint8_t* handles /*[world,64] host, rank order*/)
+{
+    PeerGroup* g = static_cast<PeerGroup*>(group);
+    if (!g || !handles) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (g->connected) return NPK_OK;
+    cudaError_t e = cudaSetDevice(g->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    npk::PeerCall pc{};
+    for (int r = 0; r < g->world; r++) {
+        if (r == g->rank) g->peer_buf[r] = g->buf;
+        else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + 64 * r, 64);
+            e = cudaIpcOpenMemHandle(&g->peer_buf[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle (are the ranks' GPUs NVLink / P2P peers on one node?)");
+        }
+        pc.flags[r] = reinterpret_cast<unsigned long long*>(g->peer_buf[r]);
+        pc.slots[r] = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(g->peer_buf[r]) + kPeerFlagBytes);
+    }
+    pc.acc = g->acc; pc.world = (uint32_t)g->world; pc.rank = (uint32_t)g->rank; pc.stride = (uint32_t)g->stride;
+    e = cudaMemcpy(g->call, &pc, sizeof pc, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(PeerCall)");
+    g->connected = true;
+    return NPK_OK;
+}
+
+int npk_peer_destroy(void* group)
+{
+    PeerGroup* g = static_cast<PeerGroup*>(group);
+    if (!g) return NPK_OK;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < g->world; r++)
+        if (r != g->rank && g->peer_buf[r]) cudaIpcCloseMemHandle(g->peer_buf[r]);
+    cudaFree(g->buf); cudaFree(g->acc); cudaFree(g->call); cudaFree(g->abort_flag);
+    delete g;
+    return NPK_OK;
+}
+
+int npk_peer_error(void* group, int* error /*host*/)
+{
+    PeerGroup* g = static_cast<PeerGroup*>(group);
+    if (!g || !error) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    unsigned int v = 0;
+    cudaError_t e = cudaMemcpy(&v, &g->call->error, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "npk_peer_error");
+    *error = (int)v;
+    return NPK_OK;
+}
+
+int npk_equity_batch_sharded(void* group, const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q,
+                             int64_t trials_total, int players, int known, uint64_t seed, int64_t query_offset,
+                             int deal_mode, uint64_t* totals, void* stream)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    PeerGroup* g = static_cast<PeerGroup*>(group);
+    if (!g || !g->connected) return fail(NPK_ERR_INVALID_ARGUMENT, "peer group not connected");
+    if (!hole || !board || !n_players || !totals) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (Q <= 0 || 2 * Q > g->stride) return fail(NPK_ERR_INVALID_ARGUMENT, "Q must be 1..max_words/2 of the peer group");
+    if (trials_total < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (players < 1 || players > 10 || known < 0 || known > 5) return fail(NPK_ERR_INVALID_CARDS, "players must be 1..10 and known board cards 0..5");
+    if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+    // this rank's trial range: the same split as neuron_poker_b200.dist.trial_shard
+    const int64_t base = trials_total / g->world, extra = trials_total % g->world;
+    const int64_t begin = g->rank * base + std::min<int64_t>(g->rank, extra);
+    const int64_t count = base + (g->rank < extra ? 1 : 0);
+    npk::EquityParams p{};
+    p.tables = ds->t;
+    p.hole = hole; p.board = board; p.n_players = n_players;
+    p.nq = Q; p.trials = count; p.trial_offset = begin; p.query_offset = (uint32_t)query_offset;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.chunk = pick_chunk(Q, std::max<int64_t>(count, 1), ds->sm_count, 64);
+    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+    p.wins = g->acc; p.ties = g->acc + Q;
+    p.abort_flag = g->abort_flag;
+    p.peer = g->call; p.peer_epoch = ++g->epoch; p.peer_totals = reinterpret_cast<unsigned long long*>(totals);
+    p.peer_words = (uint32_t)(2 * Q);
+    p.work_counter = &g->call->work_counter;
+    const long long chunks = count > 0 ? (count + p.chunk - 1) / p.chunk : 0;
+    // a rank without trials (more ranks than trials) still takes part in the exchange: one item-less CTA
+    cudaError_t e = npk::launch_equity_uniform(players - 1, 5 - known, p, std::max<long long>(Q * chunks, 1), ds->sm_count,
+                                               tuning().warps, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "equity kernel launch (sharded)");
+}
+
+}  // extern "C"
 
 // ---- ranges ------------------------------------------------------------------------------------------------------------
 __global__ void validate_ranges_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,

@@ -85,6 +85,52 @@ __device__ __forceinline__ void finish_single_call(const EquityParams& p, int la
     __threadfence_system();
 }
 
+// Trial-sharded job: the last warp of this rank's grid exchanges the counters with the other ranks over NVLink-mapped
+// peer memory and leaves the reduced totals in p.peer_totals (see PeerCall in npk_kernels.h).
+__device__ __noinline__ void finish_peer(PeerCall* pc, unsigned long long epoch, unsigned long long* totals, uint32_t words,
+                                         int lane)
+{
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+        __threadfence();                                              // this warp's atomics before its ticket
+        const unsigned int total = gridDim.x * (blockDim.x >> 5);
+        last = atomicAdd(&pc->ticket, 1u) == total - 1u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    const uint32_t world = pc->world, me = pc->rank;
+    const uint32_t parity = (uint32_t)(epoch & 1ull);
+    const size_t my_slot = ((size_t)parity * world + me) * pc->stride;
+    for (uint32_t i = lane; i < words; i += 32) {
+        const unsigned long long v = atomicExch(&pc->acc[i], 0ull);                 // read and reset for the next step
+        for (uint32_t r = 0; r < world; r++) pc->slots[r][my_slot + i] = v;         // peer stores (NVLink for r != me)
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < world)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pc->flags[lane] + parity * kMaxPeers + me), "l"(epoch) : "memory");
+    if (lane < world) {
+        const unsigned long long* f = pc->flags[me] + parity * kMaxPeers + lane;
+        const long long t0 = clock64();
+        unsigned long long seen;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+            if (seen >= epoch) break;
+            if (clock64() - t0 > (4ll << 30)) { pc->error = 1u; break; }           // ~2 s: a peer never arrived
+        }
+    }
+    __syncwarp();
+    const unsigned long long* mine = pc->slots[me] + (size_t)parity * world * pc->stride;
+    for (uint32_t i = lane; i < words; i += 32) {
+        unsigned long long s = 0;
+        for (uint32_t r = 0; r < world; r++) s += __ldcv(mine + (size_t)r * pc->stride + i);
+        totals[i] = s;
+    }
+    if (lane == 0) { pc->work_counter = 0; pc->ticket = 0; }
+}
+
 // What a complete board says about flushes: at most one suit (the one holding >= 3 board cards) can still flush.
 struct BoardFlush {
     uint32_t fsx;     // that suit << 4 (meaningless when thr == 64)
@@ -262,6 +308,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_uniform_kernel(co
         }
     }
     finish_single_call(p, lane);
+    if (p.peer) finish_peer(p.peer, p.peer_epoch, p.peer_totals, p.peer_words, lane);
 }
 
 // =====================================================================================================================
@@ -552,6 +599,7 @@ __global__ void __launch_bounds__(kEquityMaxThreads, 1) equity_refdeal_kernel(co
         }
     }
     finish_single_call(p, lane);
+    if (p.peer) finish_peer(p.peer, p.peer_epoch, p.peer_totals, p.peer_words, lane);
 }
 
 // =====================================================================================================================

@@ -26,6 +26,25 @@ struct SingleCall {               // in device memory
     SingleResult* host;
 };
 
+// Trial-sharded jobs (one query spans several GPUs): the count reduction is part of the Monte-Carlo kernel.
+// Every rank owns one PeerBuf in its own HBM, mapped into every other rank's address space (CUDA IPC over NVLink):
+//   flags[parity][r]          epoch of the last block rank r has pushed into slots[parity][r] of THIS buffer
+//   slots[parity][r][words]   rank r's counters for the step of that parity
+// The last warp of a rank's kernel pushes its counters into its slot on every rank, publishes the epoch, waits for all
+// ranks' epochs in its own buffer, sums the slots into `totals` and resets the local counters for the next step: no
+// memset, no pack kernel, no NCCL call on the step path.  Two parities are enough: a rank cannot start step s+2 before
+// every rank has pushed step s+1, which each does only after it has finished reading step s.
+constexpr int kMaxPeers = 16;
+struct PeerCall {                    // in device memory, written once when the group is connected
+    unsigned long long* flags[kMaxPeers];     // flags region of rank r's buffer: [2][kMaxPeers]
+    unsigned long long* slots[kMaxPeers];     // slots region of rank r's buffer: [2][world][stride]
+    unsigned long long* acc;                  // local counters [stride] (wins [Q], ties [Q])
+    unsigned long long work_counter;
+    unsigned int ticket;
+    unsigned int error;                       // 1: a peer's epoch did not arrive in time
+    uint32_t world, rank, stride;
+};
+
 struct EquityParams {
     DeviceTables tables;
     const uint8_t* hole;          // [Q,2] card ids
@@ -49,6 +68,11 @@ struct EquityParams {
     // ---- single blocking call (npk_equity_host with one query): no copies, no memsets ----
     uint64_t inline_query;        // hole[2] | board[5] << 16 (bytes), used when `hole` is null
     SingleCall* single;           // device scratch + mapped host result block, or null
+    // ---- trial-sharded job: reduce the counters over the ranks inside the kernel ----
+    PeerCall* peer;               // or null
+    unsigned long long peer_epoch;
+    unsigned long long* peer_totals;   // [peer_words] reduced counters (this rank's output)
+    uint32_t peer_words;
     // ---- ranges (equity_ranges_kernel only) ----
     uint32_t opp_mask[6];         // 169-bit mask of the starting-hand classes an opponent may hold
     uint32_t hero_mask[6];        // the same for the hero when hero_range != 0

@@ -99,6 +99,17 @@ def _nccl_worker(rank, world, port, ret):
         for by in ("query", "trial"):
             w, t = npk_dist.sharded_equity(hole, board, npl, 5001, seed_value=SEED, deal_mode=mode, by=by, uniform_shape=(6, 3))
             out[(mode, by)] = (w.cpu().tolist(), t.cpu().tolist())
+        # the fused path: counters exchanged over NVLink peer memory inside the kernel, several steps in a row (both
+        # parities of the exchange buffer, ranks running ahead of each other), and the NCCL variant of the same job
+        for red in ("peer", "nccl"):
+            job = npk_dist.TrialShardedJob(hole, board, npl, (6, 3), rank, world, deal_mode=mode, reduction=red)
+            steps = []
+            for i in range(5):
+                tot = job.step(5001 + i, SEED + i)
+                steps.append(tot.cpu().tolist())
+            job.check()
+            job.close()
+            out[(mode, red)] = steps
     ret[rank] = out
     dist.destroy_process_group()
 
@@ -126,3 +137,10 @@ def test_nccl_sharded_counts_equal_unsharded():
         for r in range(world):
             for by in ("query", "trial"):
                 assert ret[r][(mode, by)] == want, (mode, by, r)
+        for i in range(5):
+            one = npk.get_equity_batch(cards[:, :2].copy(), board, np.full(Q, 6, dtype=np.uint8), 5001 + i, seed_value=SEED + i,
+                                       deal_mode=mode, uniform_shape=(6, 3))
+            want = [one["wins"].cpu().tolist(), one["ties"].cpu().tolist()]
+            for r in range(world):
+                for red in ("peer", "nccl"):
+                    assert ret[r][(mode, red)][i] == want, (mode, red, r, i)
