@@ -381,15 +381,21 @@ def run_selfplay(args, wl, cx, deal, steps=None):
     N, runs = wl["queries"], wl["trials"]
     tb = HoldemTables(N, n_players=6, seed=7, table_offset=rank * N, autoplay=[1] * 6, device=dev)
     agents = EquityAgents.equity_vs_random()
-    evals = torch.zeros((), dtype=torch.int64, device=dev)
-    acted = torch.zeros((), dtype=torch.int64, device=dev)
+    # what every step asked for is recorded (one small copy kernel per step) and summed after the timed region
+    n_e2e = max(3, min(steps, 50))
+    rec = torch.zeros((steps + n_e2e, N), dtype=torch.uint8, device=dev)
+    cursor = [0]
 
     def step(count):
         tb.selfplay_step(agents, runs=runs, deal_mode=deal)
         if count:
             _, _, npl, active = tb._q
-            evals.add_((npl.to(torch.int64) * active.to(torch.int64)).sum() * runs)
-            acted.add_(active.to(torch.int64).sum())
+            torch.mul(npl, active, out=rec[cursor[0]])          # players of the query, 0 for a table without a query
+            cursor[0] += 1
+
+    def totals(lo, hi):
+        r = rec[lo:hi].to(torch.int64)
+        return torch.stack([r.sum() * runs, (r > 0).sum()])
 
     for _ in range(max(args.warmup, 30)):           # reach a steady mix of streets and player counts
         step(False)
@@ -404,17 +410,15 @@ def run_selfplay(args, wl, cx, deal, steps=None):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = cx.max_over_ranks(e0.elapsed_time(e1))
-    tot = cx.sum_over_ranks(torch.stack([evals, acted]).to(torch.float64))
+    tot = cx.sum_over_ranks(totals(0, steps).to(torch.float64))
     st = tb.state()
     # end to end: the same loop with the rewards of every step copied to the host
     w0 = time.perf_counter()
-    n_e2e = max(3, min(steps, 50))
-    ev0 = int(evals.item())
     for _ in range(n_e2e):
         step(True)
         tb.rewards.cpu()
     e2e_s = cx.max_over_ranks(time.perf_counter() - w0)
-    e2e_evals = (int(evals.item()) - ev0) * world
+    e2e_evals = float(cx.sum_over_ranks(totals(steps, steps + n_e2e).to(torch.float64))[0].item())
     return {
         "metric": METRIC, "value": float(tot[0].item()) / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": max(args.warmup, 30), "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak",
@@ -428,7 +432,7 @@ def run_selfplay(args, wl, cx, deal, steps=None):
         "clocks": clocks,
         "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * N,
                 "steps": n_e2e, "api": "HoldemTables.selfplay_step + rewards.cpu()"},
-        "gpu_launches": steps * tb.launches_per_step if hasattr(tb, "launches_per_step") else None,
+        "gpu_launches": steps * tb.launches_per_step,
     }
 
 
@@ -626,8 +630,24 @@ def run_strong(args, cx, deal="uniform", steps=10):
     same = bool(torch.equal(got[0], ref["wins"]) and torch.equal(got[1], ref["ties"]))
     same = cx.max_over_ranks(0.0 if same else 1.0) == 0.0
     assert same, "trial-sharded counters differ from the unsharded run"
+    # where the time of a sharded step goes: this rank's trial range through the plain entry point (memset + kernel, no
+    # exchange), timed the same way
+    t_off, t_cnt = npk.dist.trial_shard(wl["trials"], cx.rank, cx.world)
+    both = torch.zeros((2, len(hole_h)), dtype=torch.int64, device=cx.dev)
+    share = {"wins": both[0], "ties": both[1]}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(steps + 2):
+        if i == 2:
+            ev[0].record()
+        npk.get_equity_batch(hole, board, npl, t_cnt, seed_value=500 + i, deal_mode=deal, trial_offset=t_off,
+                             uniform_shape=(P, B), validate=False, out=share)
+    ev[1].record()
+    torch.cuda.synchronize()
+    share_ms = cx.max_over_ranks(ev[0].elapsed_time(ev[1])) / steps
     sharded["strong_scaling"] = {"ms_per_step_one_gpu_unsharded": t1, "ms_per_step_sharded": sharded["ms_per_step"],
                                  "efficiency": t1 / (cx.world * sharded["ms_per_step"]), "n_gpus": cx.world,
+                                 "ms_per_step_share_without_exchange": share_ms,
+                                 "exchange_and_skew_ms": sharded["ms_per_step"] - share_ms,
                                  "sharded_equals_unsharded_bit_exact": same,
                                  "check": "169 classes x %d trials, seed 77: reduced [2,169] counters of the %d-way trial "
                                           "split == one-GPU counters (torch.equal on the device, all ranks)" % (T, cx.world),

@@ -79,9 +79,10 @@ int64_t npk_equity_workspace_bytes(int64_t Q);
  *   hole       [Q,2]  hero cards
  *   board      [Q,5]  known table cards first, 0xFF padding (0..5 known cards)
  *   n_players  [Q]    players still in the hand including the hero (1..10)
- *   uniform_players / uniform_known: if >= 0, EVERY query has that many players / known board cards and the call is
- *                     fully asynchronous; if either is < 0 the queries are classified on the device, which costs one
- *                     small device->host read (the stream is synchronised once) before the per-shape launches.
+ *   uniform_players / uniform_known: if >= 0, EVERY query has that many players / known board cards and that shape's own
+ *                     kernel runs; if either is < 0 the queries are classified on the device and one persistent kernel
+ *                     handles all shapes.  Both are fully asynchronous unless NPK_FLAG_VALIDATE is set (one small
+ *                     device->host read, the stream is synchronised once).
  *   seed, trial_offset, query_offset: trial t of query q uses the Philox4x32-10 stream with counter
  *                     (t + trial_offset, q + query_offset) and key = seed: results do not depend on how trials or
  *                     queries are partitioned over calls or GPUs.
@@ -97,16 +98,20 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
                      void* workspace, void* stream);
 
 /*
- * The same for MIXED batches without any host round trip (self-play loops, CUDA-graph capture): the queries are classified
- * by shape on the device, and one kernel per shape named in `shape_mask` (bit (players-1)*6 + known_board_cards) is
- * enqueued; each reads the size of its group from device memory and leaves at once when the batch holds no query of its
- * shape.  Queries whose shape is not in the mask, or that are invalid, are left untouched (their counters stay as they
- * are); nothing is validated or reported.  Results are identical to npk_equity_batch.
+ * The same for MIXED batches, guaranteed free of any host round trip (self-play loops, CUDA-graph capture).  Mixed batches
+ * always run as: classification by shape on the device (two small kernels) + ONE persistent kernel that handles every shape
+ * (group after group through one work counter: the tables are staged once per CTA, there is one tail per call);
+ * npk_equity_batch does the same when the uniform_* hints are negative.  `shape_mask` (bit (players-1)*6 +
+ * known_board_cards) restricts the call to some shapes: queries of other shapes, and invalid queries, are left untouched
+ * (their counters stay as they are).  Nothing is validated or reported by this call itself;
+ * npk_equity_batch_status(workspace, stream, &invalid, &skipped) -- HOST pointers, synchronises `stream` -- returns how many
+ * queries of the LAST call on that workspace were invalid / outside the mask.  Results are identical to npk_equity_batch.
  */
 int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
                            uint64_t shape_mask, uint64_t seed, int64_t trial_offset, int64_t query_offset, int deal_mode,
                            uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
                            void* stream);
+int npk_equity_batch_status(const void* workspace, void* stream, uint32_t* invalid, uint32_t* skipped);
 
 /*
  * Trial-sharded jobs (one query spans several GPUs, e.g. 169 classes x 1,000,000 trials over 8 GPUs): the
@@ -165,27 +170,42 @@ int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint
                            uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                            uint64_t* passes);
 
+/*
+ * The evaluator entry points below take `flags`: with NPK_FLAG_VALIDATE the inputs are checked on the device first (every card
+ * id < 52, no card twice in a row, n_players in range, a shape the kernel implements) and a violation is reported as
+ * NPK_ERR_INVALID_CARDS / NPK_ERR_INVALID_ARGUMENT before anything is computed -- the stream is synchronised once.  Without
+ * the flag the CALLER guarantees valid inputs: the kernels stay memory-safe for any byte values (ids are clamped to the
+ * 64-slot descriptor table) but the results for invalid rows are meaningless.  The reference's error behaviour for this
+ * case is a ValueError / RuntimeError("Card Type error!") (montecarlo_python.py:127-128, Montecarlo.cpp:233).
+ */
 /* rank ids of N 7-card hands */
-int npk_rank7_batch(const uint8_t* cards /*[N,7]*/, int64_t N, uint16_t* ranks /*[N]*/, void* stream);
+int npk_rank7_batch(const uint8_t* cards /*[N,7]*/, int64_t N, uint16_t* ranks /*[N]*/, uint32_t flags, void* stream);
 /* rank ids of the 7-card hands number first..first+count-1 in colexicographic order of C(52,7) = 133,784,560 hands
  * (c0<...<c6, index = sum C(c_i, i+1)) -- no input traffic; for the exhaustive parity check */
 int npk_rank7_colex(int64_t first, int64_t count, uint16_t* ranks, void* stream);
 
 /* Exact enumeration: heads-up (n_players = 2) with 0..5 known board cards, or three players on a complete board.
  * win/tie/lose [Q] u64 are overwritten: hero strictly best / tied / beaten, over all completions x opponent hands
- * (ordered pairs of disjoint hands for three players). */
+ * (ordered pairs of disjoint hands for three players).  A query of any other shape gets 0 / 0 / 0 (NPK_FLAG_VALIDATE
+ * reports it as NPK_ERR_INVALID_ARGUMENT instead). */
 int npk_enum_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, uint64_t* win,
-                   uint64_t* tie, uint64_t* lose, void* stream);
+                   uint64_t* tie, uint64_t* lose, uint32_t flags, void* stream);
 
 /* Batched showdown: holes [N,maxp,2], n_players [N] (1..maxp), board [N,5] complete.  winner [N] = first index among the
  * best hands (hand_evaluator.py:23 stable sort), wtype [N] = its hand type 0..8, ranks [N,maxp] or NULL. */
 int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uint8_t* board, int64_t N, int maxp,
-                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, void* stream);
+                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, uint32_t flags, void* stream);
 
 /* Integer-issue microbenchmark on the current device (the roofline denominator of the Monte-Carlo kernel):
  * variant 0 = LOP3 chains (alu pipe), 1 = IMAD chains (fma pipe), 2 = both interleaved.  Reports executed
  * thread-instructions per second (best of 3 timed launches after a warm-up) and that launch's duration. */
 int npk_int_peak(int variant, int iters, double* thread_instr_per_s, float* ms);
+
+/* HOST, synchronises the device.  checked_build = 1 when the library was compiled with -DNPK_CHECKED (bounds checks on every
+ * shared-memory gather, deck slot and decoded index of the kernels, deck-restored check after every work item: the stand-in
+ * for compute-sanitizer where that tool is unavailable); first_failure = highest code of a failed check since npk_init
+ * (0 = none; codes in csrc/npk_device.cuh).  Always 0 in the normal build. */
+int npk_checked_status(int* checked_build, uint32_t* first_failure);
 
 /* Philox4x32-10 known-answer hook: out[4i..4i+3] = philox(counter ctr[4i..4i+3], key (k0,k1)) */
 int npk_philox_debug(const uint32_t* ctr, uint32_t k0, uint32_t k1, int n, uint32_t* out, void* stream);

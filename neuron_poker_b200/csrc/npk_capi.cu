@@ -22,22 +22,11 @@ namespace {
 thread_local std::string g_err;
 std::mutex g_mu;
 
-constexpr int kGroupStreams = 60;   // one per (opponents, known board cards) shape of a mixed batch
-
 struct DeviceState {
     bool ready = false;
     int sm_count = 0;
     npk::DeviceTables t{};
     void* blob = nullptr;
-    // one-query blocking calls (npk_equity_host, Q == 1): counters in device memory, results in mapped host memory
-    npk::SingleCall* single = nullptr;
-    npk::SingleResult* single_host = nullptr;
-    cudaStream_t single_stream = nullptr;
-    // mixed batches: the per-shape kernels run side by side, each on its share of the SMs
-    bool streams_ready = false;
-    cudaStream_t group_stream[kGroupStreams] = {};
-    cudaEvent_t group_done[kGroupStreams] = {};
-    cudaEvent_t fork = nullptr;
 };
 
 npk::Tables g_tables;
@@ -45,8 +34,8 @@ bool g_tables_ready = false;
 constexpr int kMaxDevices = 64;
 DeviceState g_dev[kMaxDevices];
 
-// host-staging state of npk_equity_host (one per process, guarded by g_host_mu)
-std::mutex g_host_mu;
+// host-staging state of npk_equity_host: one per CALLING THREAD (its own stream, pinned buffers and one-query scratch), so
+// the host entry point is re-entrant -- two host threads never share a stream, a counter or a result block
 struct HostStage {
     int device = -1;
     int64_t cap_q = 0;
@@ -56,19 +45,34 @@ struct HostStage {
     uint64_t* d_out = nullptr;
     void* d_ws = nullptr;
     cudaStream_t stream = nullptr;
-} g_stage;
+    // one-query blocking calls (Q == 1): counters in device memory, results in mapped host memory
+    npk::SingleCall* single = nullptr;
+    npk::SingleResult* single_host = nullptr;
+    void release()
+    {
+        if (device < 0) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { device = -1; return; }     // runtime already torn down
+        cudaSetDevice(device);
+        cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
+        cudaFree(single); cudaFreeHost(single_host);
+        if (stream) cudaStreamDestroy(stream);
+        if (cur >= 0) cudaSetDevice(cur);
+        *this = HostStage{};
+    }
+    ~HostStage() { release(); }
+};
+thread_local HostStage t_stage;
 
 // Tuning aids, read from the environment ONCE (a getenv per launch costs as much as the launch of a 30 us call).
 struct Tuning {
     long long chunk = 0;        // NPK_CHUNK: trials per work item
     int warps = 0;              // NPK_WARPS: warps per CTA of the Monte-Carlo kernels
-    bool serial_groups = false; // NPK_SERIAL_GROUPS: mixed batches one shape after another instead of side by side
     bool no_single_path = false;// NPK_NO_SINGLE_PATH: one-query host calls through the general path
     Tuning()
     {
         if (const char* e = getenv("NPK_CHUNK")) chunk = atoll(e);
         if (const char* e = getenv("NPK_WARPS")) warps = atoi(e);
-        serial_groups = getenv("NPK_SERIAL_GROUPS") != nullptr;
         no_single_path = getenv("NPK_NO_SINGLE_PATH") != nullptr;
     }
 };
@@ -112,12 +116,13 @@ int current_state(DeviceState** out)
 
 // ---- query classification (mixed player counts / board sizes) --------------------------------------------------------
 // workspace layout (bytes): [0,512) 64 work counters u64 | [512,768) 64 group counts u32 | [768,1024) 64 group offsets u32
-//                           (exclusive prefix of the counts, sync-free mixed batches; a kernel reads its group as
-//                           {count = group[0], offset = group[64]}) | [1024,1028) invalid-query count
-//                           | [1028,1092) abort flag + diagnostics | [1280,1536) 64 fill cursors u32 | [2048, 2048+4Q) qindex
-constexpr int kWsCounters = 0, kWsCounts = 512, kWsOffsets = 768, kWsInvalid = 1024, kWsAbort = 1028, kWsCursors = 1280,
-              kWsIndex = 2048;
-constexpr int kGroups = 60;   // group = nopp * 6 + known, nopp 0..9, known 0..5
+//                           (exclusive prefix of the counts; a kernel reads its group as {count = group[0], offset =
+//                           group[64]}) | [1024,1028) invalid-query count | [1028,1092) abort flag + diagnostics
+//                           | [1092,1096) queries of shapes outside the caller's shape mask | [1096,1100) blocks done
+//                           | [1280,1536) 64 fill cursors u32 | [2048, 2048+4Q) qindex
+constexpr int kWsCounters = 0, kWsCounts = 512, kWsOffsets = 768, kWsInvalid = 1024, kWsAbort = 1028, kWsSkipped = 1092,
+              kWsBlocksDone = 1096, kWsCursors = 1280, kWsIndex = 2048;
+constexpr int kGroups = npk::kShapeGroups;   // group = nopp * 6 + known, nopp 0..9, known 0..5
 
 __device__ __forceinline__ int classify_query(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
                                               long long q)
@@ -142,60 +147,91 @@ __device__ __forceinline__ int classify_query(const uint8_t* hole, const uint8_t
     return bad ? -1 : (np - 1) * 6 + known;
 }
 
-__global__ void classify_count_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
-                                      uint8_t* ws)
+// Count the queries of every shape -- per block in shared memory, then one global atomic per shape and block (65,536
+// self-play queries fall into a dozen shapes: per-query global atomics on a dozen addresses took 35 us) -- and let the last
+// block to finish drop the shapes outside `shape_mask` and write the exclusive prefix of the counts behind them.
+__global__ void __launch_bounds__(256) classify_count_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
+                                                             long long Q, uint8_t* ws, unsigned long long shape_mask)
 {
+    __shared__ uint32_t s_cnt[65];                         // [64] = invalid
+    __shared__ bool last;
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + kWsCounts);
-    uint32_t* invalid = reinterpret_cast<uint32_t*>(ws + kWsInvalid);
+    if (threadIdx.x < 65) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
         const int g = classify_query(hole, board, n_players, q);
-        if (g < 0) atomicAdd(invalid, 1u); else atomicAdd(&counts[g], 1u);
+        atomicAdd(&s_cnt[g < 0 ? 64 : g], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(&counts[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 64 && s_cnt[64]) atomicAdd(reinterpret_cast<uint32_t*>(ws + kWsInvalid), s_cnt[64]);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(reinterpret_cast<uint32_t*>(ws + kWsBlocksDone), 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + kWsOffsets);
+        uint32_t acc = 0, skipped = 0;
+        for (int g = 0; g < 64; g++) {
+            uint32_t c = *reinterpret_cast<volatile uint32_t*>(&counts[g]);
+            if (!(shape_mask >> g & 1ull)) { skipped += c; c = 0; counts[g] = 0; }
+            offsets[g] = acc;
+            acc += c;
+        }
+        *reinterpret_cast<uint32_t*>(ws + kWsSkipped) = skipped;
     }
 }
 
-struct GroupOffsets { uint32_t off[64]; };
-
-// sync-free mixed batches: exclusive prefix of the group counts, written right behind them
-__global__ void group_offsets_kernel(uint8_t* ws)
+// Sort the query numbers by shape: a block counts its own queries per shape, reserves one range per shape in qindex with a
+// single global atomic, and its threads take slots inside the range from shared-memory cursors.
+__global__ void __launch_bounds__(256) classify_fill_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
+                                                            long long Q, uint8_t* ws)
 {
-    const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
-    uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + kWsOffsets);
-    if (threadIdx.x == 0) {
-        uint32_t acc = 0;
-        for (int g = 0; g < 64; g++) { offsets[g] = acc; acc += counts[g]; }
-    }
-}
-
-__global__ void classify_fill_dev_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
-                                         uint8_t* ws)
-{
+    __shared__ uint32_t s_cnt[64], s_base[64];
     uint32_t* cursors = reinterpret_cast<uint32_t*>(ws + kWsCursors);
+    const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
     const uint32_t* offsets = reinterpret_cast<const uint32_t*>(ws + kWsOffsets);
     int32_t* qindex = reinterpret_cast<int32_t*>(ws + kWsIndex);
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
-        const int g = classify_query(hole, board, n_players, q);
-        if (g < 0) continue;
-        qindex[offsets[g] + atomicAdd(&cursors[g], 1u)] = (int32_t)q;
+    // every block handles ONE contiguous span of queries, each thread at most kPerThread of them (held in registers
+    // between the counting and the placing pass)
+    constexpr int kPerThread = 8;
+    const long long per_block = (Q + gridDim.x - 1) / gridDim.x;
+    const long long q0 = (long long)blockIdx.x * per_block, q1 = min(Q, q0 + per_block);
+    for (long long base = q0; base < q1; base += (long long)blockDim.x * kPerThread) {
+        if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int g[kPerThread];
+        uint32_t slot[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const long long q = base + (long long)k * blockDim.x + threadIdx.x;
+            g[k] = -1;
+            if (q < q1) {
+                g[k] = classify_query(hole, board, n_players, q);
+                if (g[k] >= 0 && counts[g[k]] == 0) g[k] = -1;          // a shape outside the caller's mask
+                if (g[k] >= 0) slot[k] = atomicAdd(&s_cnt[g[k]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 64 && s_cnt[threadIdx.x])
+            s_base[threadIdx.x] = offsets[threadIdx.x] + atomicAdd(&cursors[threadIdx.x], s_cnt[threadIdx.x]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++)
+            if (g[k] >= 0) qindex[s_base[g[k]] + slot[k]] = (int32_t)(base + (long long)k * blockDim.x + threadIdx.x);
+        __syncthreads();
     }
 }
 
-__global__ void classify_fill_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, long long Q,
-                                     uint8_t* ws, GroupOffsets go)
-{
-    uint32_t* cursors = reinterpret_cast<uint32_t*>(ws + kWsCursors);
-    int32_t* qindex = reinterpret_cast<int32_t*>(ws + kWsIndex);
-    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
-        const int g = classify_query(hole, board, n_players, q);
-        if (g < 0) continue;
-        qindex[go.off[g] + atomicAdd(&cursors[g], 1u)] = (int32_t)q;
-    }
-}
-
-// Trials per work item.  Large jobs use up to 2,048 (64 trials per lane: the per-item set-up -- query load, deck
-// initialisation, reduction -- is then about 1 % of the work) but at least eight items per warp, so the last wave of
-// items costs a few per cent at most; small jobs are cut finer so that a single query still spreads over the whole
-// chip (a lone get_equity call of 10,000 trials becomes 313 one-iteration items).
-uint32_t pick_chunk(long long queries, long long trials, int sm_count, int lanes_worth = 32)
+// Work items of a launch: (query, chunk of trials).  Items hold up to 2,048 trials (64 per lane: the per-item set-up --
+// query load, deck initialisation, reduction -- is then a few per cent of the work) but at least eight per warp; small jobs
+// are cut finer so that a single query still spreads over the whole chip (a lone get_equity call of 10,000 trials becomes 157
+// one-iteration items).  A finer-grained tail (the last eighth of every query in items an eighth of the size, handed out
+// last) was measured in round 2 and lost 1.5 % on cfg3: the warps left over in the last round of items run faster, because
+// the SM is throughput-bound, so the tail costs about 1 %, less than the extra item set-ups.
+// Returns the number of items per query.
+long long plan_items(npk::EquityParams& p, long long queries, long long trials, int sm_count, int lanes_worth = 64)
 {
     const long long warps = (long long)sm_count * 16;
     long long c = (queries * trials) / (8 * warps);
@@ -203,8 +239,11 @@ uint32_t pick_chunk(long long queries, long long trials, int sm_count, int lanes
     c = (c + lanes_worth - 1) / lanes_worth * lanes_worth;      // a warp iteration covers 64 trials (a pair per lane)
     if (c < lanes_worth) c = lanes_worth;
     if (c > 2048) c = 2048;
-    if (trials <= c) return (uint32_t)(trials > 0 ? trials : 1);
-    return (uint32_t)c;
+    if (trials <= 0) { p.chunk = 1; p.chunks = 0; return 0; }
+    if (trials <= c) { p.chunk = (uint32_t)trials; p.chunks = 1; return 1; }
+    p.chunk = (uint32_t)c;
+    p.chunks = (uint32_t)((trials + c - 1) / c);
+    return p.chunks;
 }
 
 int grid_for(const DeviceState& ds, long long items, int warps_per_cta)
@@ -268,6 +307,9 @@ int npk_init(int device)
     ds.t.rowoff_bytes = (uint32_t)rb;
     ds.t.flush_bytes = (uint32_t)fb;
     for (int i = 0; i < 10; i++) ds.t.type_start[i] = g_tables.type_start[i];
+    e = cudaMalloc(&ds.t.check, 4);
+    if (e == cudaSuccess) e = cudaMemset(ds.t.check, 0, 4);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(check word)");
     ds.ready = true;
     return NPK_OK;
 }
@@ -287,23 +329,28 @@ int npk_shutdown(void)
         if (!g_dev[d].ready) continue;
         cudaSetDevice(d);
         cudaFree(g_dev[d].blob);
-        if (g_dev[d].single) {
-            cudaFree(g_dev[d].single); cudaFreeHost(g_dev[d].single_host); cudaStreamDestroy(g_dev[d].single_stream);
-        }
-        if (g_dev[d].streams_ready) {
-            for (int g = 0; g < kGroupStreams; g++) { cudaStreamDestroy(g_dev[d].group_stream[g]); cudaEventDestroy(g_dev[d].group_done[g]); }
-            cudaEventDestroy(g_dev[d].fork);
-        }
+        cudaFree(g_dev[d].t.check);
         g_dev[d] = DeviceState{};
     }
-    std::lock_guard<std::mutex> lk2(g_host_mu);
-    if (g_stage.device >= 0) {
-        cudaSetDevice(g_stage.device);
-        cudaFreeHost(g_stage.h_in); cudaFreeHost(g_stage.h_out);
-        cudaFree(g_stage.d_in); cudaFree(g_stage.d_out); cudaFree(g_stage.d_ws);
-        if (g_stage.stream) cudaStreamDestroy(g_stage.stream);
-        g_stage = HostStage{};
-    }
+    t_stage.release();            // the calling thread's staging; other threads release theirs when they exit
+    return NPK_OK;
+}
+
+int npk_checked_status(int* checked_build, uint32_t* first_failure)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+#ifdef NPK_CHECKED
+    if (checked_build) *checked_build = 1;
+#else
+    if (checked_build) *checked_build = 0;
+#endif
+    uint32_t v = 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(&v, ds->t.check, 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "npk_checked_status");
+    if (first_failure) *first_failure = v;
     return NPK_OK;
 }
 
@@ -343,6 +390,24 @@ int npk_host_rank7(const uint8_t* cards, int64_t n, uint16_t* ranks)
 
 int64_t npk_equity_workspace_bytes(int64_t Q) { return kWsIndex + 4 * (Q > 0 ? Q : 0) + 64; }
 
+namespace {
+// Mixed batch: classify on the device (two small kernels), then ONE persistent kernel for all shapes (npk_mixed.cu).
+// Nothing is read back: asynchronous on `s`.
+int enqueue_mixed(DeviceState* ds, npk::EquityParams& p, const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
+                  int64_t Q, uint64_t shape_mask, uint8_t* ws, cudaStream_t s)
+{
+    const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
+    classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws, shape_mask);
+    classify_fill_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
+    p.group = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
+    p.qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
+    p.nq = 0;
+    p.work_counter = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+    cudaError_t e = npk::launch_equity_mixed(p, ds->sm_count, s);
+    return e == cudaSuccess ? NPK_OK : cuda_fail(e, "equity_mixed_kernel launch");
+}
+}  // namespace
+
 int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
                      int uniform_players, int uniform_known, uint64_t seed, int64_t trial_offset, int64_t query_offset,
                      int deal_mode, uint32_t flags, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
@@ -371,20 +436,24 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count, 64);
+    const long long chunks = plan_items(p, Q, trials, ds->sm_count);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
     p.passes = deal_mode == NPK_DEAL_REFERENCE ? reinterpret_cast<unsigned long long*>(passes) : nullptr;
-    const long long chunks = (trials + p.chunk - 1) / p.chunk;
-    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+    p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);      // + 15 diagnostic words, all inside the header
+    const bool validate = (flags & NPK_FLAG_VALIDATE) != 0;
 
-    uint32_t counts[64];
-    std::memset(counts, 0, sizeof counts);
-    const bool need_classes = !uniform_shape || (flags & NPK_FLAG_VALIDATE);   // both dealers are shape-specialised
-    if (need_classes) {
+    if (uniform_shape && !validate) {
+        p.qindex = nullptr; p.nq = Q; p.work_counter = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
+        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p, Q * chunks, ds->sm_count, tuning().warps, s);
+        return e == cudaSuccess ? NPK_OK : cuda_fail(e, "equity_uniform_kernel launch");
+    }
+    if (uniform_shape) {
+        // validated: classify first (one small device->host read), then the shape's own kernel
         const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
-        classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
+        classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws, ~0ull);
         uint32_t host[64 + 64 + 1];
         e = cudaMemcpyAsync(host, ws + kWsCounts, 4 * 129, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -392,72 +461,21 @@ int npk_equity_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n
         if (host[128]) return fail(NPK_ERR_INVALID_CARDS, std::to_string(host[128]) +
                                    " invalid quer" + (host[128] == 1 ? "y" : "ies") +
                                    " (card id >= 52, duplicate cards, gap in the board, or players outside 1..10)");
-        std::memcpy(counts, host, sizeof counts);
-        if (uniform_shape && counts[(uniform_players - 1) * 6 + uniform_known] != (uint32_t)Q)
+        if (host[(uniform_players - 1) * 6 + uniform_known] != (uint32_t)Q)
             return fail(NPK_ERR_INVALID_ARGUMENT, "queries do not all have the declared uniform shape");
+        p.qindex = nullptr; p.nq = Q; p.work_counter = reinterpret_cast<unsigned long long*>(ws + kWsCounters) + 1;
+        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p, Q * chunks, ds->sm_count, tuning().warps, s);
+        return e == cudaSuccess ? NPK_OK : cuda_fail(e, "equity_uniform_kernel launch");
     }
-
-    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
-    p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);      // + 15 diagnostic words, all inside the header
-
-    const int forced_warps = tuning().warps;
-    if (uniform_shape) {
-        p.qindex = nullptr; p.nq = Q; p.work_counter = counters;
-        e = npk::launch_equity_uniform(uniform_players - 1, 5 - uniform_known, p, Q * chunks, ds->sm_count, forced_warps, s);
-        if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
-        return NPK_OK;
-    }
-
-    GroupOffsets go;
-    uint32_t acc = 0;
-    for (int g = 0; g < 64; g++) { go.off[g] = acc; acc += counts[g]; }
-    {
-        const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
-        classify_fill_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws, go);
-    }
-    // One kernel per shape, all running side by side: every shape gets a share of the SMs proportional to its work
-    // (queries x algorithmic instructions per trial), so the launches finish together instead of queueing
-    // twenty under-filled grids one after another.
-    int n_groups = 0;
-    double weight[kGroups], total_weight = 0;
-    for (int g = 0; g < kGroups; g++) {
-        weight[g] = 0;
-        if (!counts[g]) continue;
-        const int players = g / 6 + 1, d = 2 * (players - 1) + (5 - g % 6);
-        weight[g] = (double)counts[g] * (64.0 * ((d + 7) / 8) + 8.0 * d + 15.0 * players + 3.0);
-        total_weight += weight[g];
-        n_groups++;
-    }
-    const bool side_by_side = n_groups > 1 && !tuning().serial_groups;
-    if (side_by_side && !ds->streams_ready) {
-        for (int g = 0; g < kGroupStreams; g++) {
-            if ((e = cudaStreamCreateWithFlags(&ds->group_stream[g], cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
-            if ((e = cudaEventCreateWithFlags(&ds->group_done[g], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
-        }
-        if ((e = cudaEventCreateWithFlags(&ds->fork, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
-        ds->streams_ready = true;
-    }
-    if (side_by_side && (e = cudaEventRecord(ds->fork, s)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-    const int32_t* qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
-    for (int g = 0; g < kGroups; g++) {
-        if (!counts[g]) continue;
-        const int nopp = g / 6, known = g % 6;
-        p.qindex = qindex + go.off[g]; p.nq = counts[g]; p.work_counter = counters + g;
-        cudaStream_t gs = s;
-        int sms = ds->sm_count;
-        if (side_by_side) {
-            gs = ds->group_stream[g];
-            sms = (int)(ds->sm_count * weight[g] / total_weight + 0.5);
-            if (sms < 1) sms = 1;
-            if ((e = cudaStreamWaitEvent(gs, ds->fork, 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-        }
-        e = npk::launch_equity_uniform(nopp, 5 - known, p, p.nq * chunks, sms, forced_warps, gs);
-        if (e != cudaSuccess) return cuda_fail(e, "equity_uniform_kernel launch");
-        if (side_by_side) {
-            if ((e = cudaEventRecord(ds->group_done[g], gs)) != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
-            if ((e = cudaStreamWaitEvent(s, ds->group_done[g], 0)) != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
-        }
-    }
+    rc = enqueue_mixed(ds, p, hole, board, n_players, Q, ~0ull, ws, s);
+    if (rc || !validate) return rc;
+    uint32_t bad = 0;
+    e = cudaMemcpyAsync(&bad, ws + kWsInvalid, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "mixed batch");
+    if (bad) return fail(NPK_ERR_INVALID_CARDS, std::to_string(bad) + " invalid quer" + (bad == 1 ? "y" : "ies") +
+                         " (card id >= 52, duplicate cards, gap in the board, or players outside 1..10); their counters "
+                         "are untouched, the other queries have been computed");
     return NPK_OK;
 }
 
@@ -482,37 +500,36 @@ int npk_equity_batch_async(const uint8_t* hole, const uint8_t* board, const uint
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     cudaError_t e = cudaMemsetAsync(ws, 0, kWsIndex, s);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
-    const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
-    classify_count_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
-    group_offsets_kernel<<<1, 32, 0, s>>>(ws);
-    classify_fill_dev_kernel<<<cg, 256, 0, s>>>(hole, board, n_players, Q, ws);
-
     npk::EquityParams p{};
     p.tables = ds->t;
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count, 64);
+    plan_items(p, Q, trials, ds->sm_count);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
     p.passes = deal_mode == NPK_DEAL_REFERENCE ? reinterpret_cast<unsigned long long*>(passes) : nullptr;
     p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
     p.abort_flag = reinterpret_cast<uint32_t*>(ws + kWsAbort);
-    p.qindex = reinterpret_cast<const int32_t*>(ws + kWsIndex);
-    p.nq = 0;
-    const long long chunks = (trials + p.chunk - 1) / p.chunk;
-    const int forced_warps = tuning().warps;
-    unsigned long long* counters = reinterpret_cast<unsigned long long*>(ws + kWsCounters);
-    const uint32_t* counts = reinterpret_cast<const uint32_t*>(ws + kWsCounts);
-    for (int g = 0; g < kGroups; g++) {
-        if (!(shape_mask >> g & 1ull)) continue;
-        p.group = counts + g;                    // {count, offset} of this shape, read by the kernel itself
-        p.work_counter = counters + g;
-        // the group's size is unknown on the host: every shape gets the whole chip, an empty one leaves at once
-        e = npk::launch_equity_uniform(g / 6, 5 - g % 6, p, Q * chunks, ds->sm_count, forced_warps, s);
-        if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
-    }
+    return enqueue_mixed(ds, p, hole, board, n_players, Q, shape_mask, ws, s);
+}
+
+int npk_equity_batch_status(const void* workspace, void* stream, uint32_t* invalid, uint32_t* skipped)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (!workspace) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    const uint8_t* ws = static_cast<const uint8_t*>(workspace);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t v[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(&v[0], ws + kWsInvalid, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&v[1], ws + kWsSkipped, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "npk_equity_batch_status");
+    if (invalid) *invalid = v[0];
+    if (skipped) *skipped = v[1];
     return NPK_OK;
 }
 
@@ -527,8 +544,13 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     if (!hole || !board || !n_players || !wins_strict || !ties) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lk(g_host_mu);
+    HostStage& st = t_stage;                       // this thread's staging: no lock, no shared stream
+    if (st.device != dev) st.release();
     cudaError_t e;
+    if (st.device < 0) {
+        if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        st.device = dev;
+    }
     if (Q == 1 && !tuning().no_single_path) {
         // One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in
         // device memory between calls (the last warp hands them over and zeroes them), the result lands in mapped host
@@ -551,15 +573,14 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
         if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
             return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
         if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
-        if (!ds->single) {
-            if ((e = cudaStreamCreateWithFlags(&ds->single_stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
-            if ((e = cudaHostAlloc(&ds->single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+        if (!st.single) {
+            if ((e = cudaHostAlloc(&st.single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
             npk::SingleResult* dptr = nullptr;
-            if ((e = cudaHostGetDevicePointer(&dptr, ds->single_host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
-            if ((e = cudaMalloc(&ds->single, sizeof(npk::SingleCall))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+            if ((e = cudaHostGetDevicePointer(&dptr, st.single_host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+            if ((e = cudaMalloc(&st.single, sizeof(npk::SingleCall))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
             npk::SingleCall init{};
             init.host = dptr;
-            if ((e = cudaMemcpy(ds->single, &init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+            if ((e = cudaMemcpy(st.single, &init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
         }
         wins_strict[0] = 0; ties[0] = 0;
         if (win_types) std::memset(win_types, 0, 72);
@@ -572,42 +593,34 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
         for (int i = 0; i < 5; i++) p.inline_query |= (uint64_t)board[i] << (16 + 8 * i);
         p.nq = 1; p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
         p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-        p.chunk = pick_chunk(1, trials, ds->sm_count, 64);
+        const long long chunks = plan_items(p, 1, trials, ds->sm_count);
         p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
-        p.single = ds->single;
-        p.work_counter = &ds->single->work_counter;
-        p.wins = &ds->single->wins; p.ties = &ds->single->ties;
-        p.win_types = win_types ? ds->single->win_types : nullptr;
-        p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &ds->single->passes : nullptr;
-        p.abort_flag = ds->single->abort_flag;
-        const long long chunks = (trials + p.chunk - 1) / p.chunk;
+        p.single = st.single;
+        p.work_counter = &st.single->work_counter;
+        p.wins = &st.single->wins; p.ties = &st.single->ties;
+        p.win_types = win_types ? st.single->win_types : nullptr;
+        p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &st.single->passes : nullptr;
+        p.abort_flag = st.single->abort_flag;
         const int forced_warps = tuning().warps;
-        e = npk::launch_equity_uniform(n_players[0] - 1, 5 - known, p, chunks, ds->sm_count, forced_warps, ds->single_stream);
+        e = npk::launch_equity_uniform(n_players[0] - 1, 5 - known, p, chunks, ds->sm_count, forced_warps, st.stream);
         if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
-        if ((e = cudaStreamSynchronize(ds->single_stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
-        const npk::SingleResult* r = ds->single_host;
+        if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
+        const npk::SingleResult* r = st.single_host;
         wins_strict[0] = r->wins; ties[0] = r->ties;
         if (win_types) for (int i = 0; i < 9; i++) win_types[i] = r->win_types[i];
         if (passes) passes[0] = r->passes;
         return NPK_OK;
     }
-    HostStage& st = g_stage;
-    if (st.device != dev || st.cap_q < Q) {
-        if (st.device >= 0) {
-            cudaSetDevice(st.device);
-            cudaFreeHost(st.h_in); cudaFreeHost(st.h_out); cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_ws);
-            if (st.stream) cudaStreamDestroy(st.stream);
-            cudaSetDevice(dev);
-        }
-        st = HostStage{};
+    if (st.cap_q < Q) {
+        cudaFreeHost(st.h_in); cudaFreeHost(st.h_out); cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_ws);
+        st.h_in = nullptr; st.h_out = nullptr; st.d_in = nullptr; st.d_out = nullptr; st.d_ws = nullptr; st.cap_q = 0;
         const int64_t cap = Q < 1024 ? 1024 : Q;
-        if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
         if ((e = cudaMallocHost(&st.h_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
         if ((e = cudaMallocHost(&st.h_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
         if ((e = cudaMalloc(&st.d_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
         if ((e = cudaMalloc(&st.d_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
         if ((e = cudaMalloc(&st.d_ws, npk_equity_workspace_bytes(cap))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        st.device = dev; st.cap_q = cap;
+        st.cap_q = cap;
     }
     std::memcpy(st.h_in, hole, 2 * Q);
     std::memcpy(st.h_in + 2 * Q, board, 5 * Q);
@@ -781,14 +794,13 @@ int npk_equity_batch_sharded(void* group, const uint8_t* hole, const uint8_t* bo
     p.hole = hole; p.board = board; p.n_players = n_players;
     p.nq = Q; p.trials = count; p.trial_offset = begin; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, std::max<int64_t>(count, 1), ds->sm_count, 64);
+    const long long chunks = plan_items(p, Q, count, ds->sm_count);
     p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
     p.wins = g->acc; p.ties = g->acc + Q;
     p.abort_flag = g->abort_flag;
     p.peer = g->call; p.peer_epoch = ++g->epoch; p.peer_totals = reinterpret_cast<unsigned long long*>(totals);
     p.peer_words = (uint32_t)(2 * Q);
     p.work_counter = &g->call->work_counter;
-    const long long chunks = count > 0 ? (count + p.chunk - 1) / p.chunk : 0;
     // a rank without trials (more ranks than trials) still takes part in the exchange: one item-less CTA
     cudaError_t e = npk::launch_equity_uniform(players - 1, 5 - known, p, std::max<long long>(Q * chunks, 1), ds->sm_count,
                                                tuning().warps, static_cast<cudaStream_t>(stream));
@@ -864,7 +876,7 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
     p.hole = hero_allowed ? nullptr : hole; p.board = board; p.n_players = n_players; p.ghost = ghost;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-    p.chunk = pick_chunk(Q, trials, ds->sm_count);
+    const long long chunks = plan_items(p, Q, trials, ds->sm_count, 32);
     p.wins = reinterpret_cast<unsigned long long*>(wins_strict);
     p.ties = reinterpret_cast<unsigned long long*>(ties);
     p.win_types = reinterpret_cast<unsigned long long*>(win_types);
@@ -892,7 +904,6 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
                              " (card id >= 52, duplicate cards, gap in the board, ghost card on the board or in the "
                              "hand, or players outside 1..10)");
     }
-    const long long chunks = (trials + p.chunk - 1) / p.chunk;
     e = npk::launch_equity_ranges(deal_mode, p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
     if (e != cudaSuccess) return cuda_fail(e, "equity_ranges_kernel launch");
     if (validate) {
@@ -947,12 +958,74 @@ int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint
     return NPK_OK;
 }
 
-int npk_rank7_batch(const uint8_t* cards, int64_t N, uint16_t* ranks, void* stream)
+// ---- validation of the evaluator entry points (NPK_FLAG_VALIDATE) -----------------------------------------------------------
+// rows of `len` card ids: every id < 52 and no id twice.  enum_mode: the row is hole[2] + board[5] (0xFF padding allowed
+// at the end of the board only) and the shape must be one enum_kernel implements.
+__global__ void check_rows_kernel(const uint8_t* a, int len_a, const uint8_t* b, int len_b, const uint8_t* n_players,
+                                  int maxp, int enum_mode, long long n, uint32_t* bad /*[2]: cards, shape*/)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long mask = 0;
+        int wrong = 0, known = 0;
+        bool ended = false;
+        int na = len_a;
+        if (maxp > 0) {                                       // showdown: only the first n_players hands count
+            const int np = n_players[i];
+            if (np < 1 || np > maxp) { atomicAdd(&bad[1], 1u); continue; }
+            na = 2 * np;
+        }
+        for (int k = 0; k < na; k++) {
+            const int c = a[(long long)len_a * i + k];
+            if (c >= 52) wrong = 1; else { wrong |= (int)(mask >> c & 1ull); mask |= 1ull << c; }
+        }
+        for (int k = 0; k < len_b; k++) {
+            const int c = b[(long long)len_b * i + k];
+            if (enum_mode && c == 0xFF) { ended = true; continue; }
+            if (ended || c >= 52) { wrong = 1; continue; }
+            wrong |= (int)(mask >> c & 1ull);
+            mask |= 1ull << c;
+            known++;
+        }
+        if (wrong) atomicAdd(&bad[0], 1u);
+        if (enum_mode) {
+            const int np = n_players[i];
+            if (!(np == 2 || (np == 3 && known == 5))) atomicAdd(&bad[1], 1u);
+        }
+    }
+}
+
+namespace {
+int check_rows(DeviceState* ds, const uint8_t* a, int len_a, const uint8_t* b, int len_b, const uint8_t* n_players, int maxp,
+               int enum_mode, int64_t n, cudaStream_t s, const char* shape_msg)
+{
+    uint32_t* d_bad = nullptr;
+    cudaError_t e = cudaMalloc(&d_bad, 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, 8, s);
+    if (e != cudaSuccess) { cudaFree(d_bad); return cuda_fail(e, "validation scratch"); }
+    const int grid = (int)std::min<long long>((n + 255) / 256, 8 * ds->sm_count);
+    check_rows_kernel<<<grid, 256, 0, s>>>(a, len_a, b, len_b, n_players, maxp, enum_mode, n, d_bad);
+    uint32_t bad[2] = {0, 0};
+    e = cudaMemcpyAsync(bad, d_bad, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return cuda_fail(e, "validation");
+    if (bad[0]) return fail(NPK_ERR_INVALID_CARDS, std::to_string(bad[0]) + " row(s) with a card id >= 52, a duplicate card or a gap in the board");
+    if (bad[1]) return fail(NPK_ERR_INVALID_ARGUMENT, std::to_string(bad[1]) + shape_msg);
+    return NPK_OK;
+}
+}  // namespace
+
+int npk_rank7_batch(const uint8_t* cards, int64_t N, uint16_t* ranks, uint32_t flags, void* stream)
 {
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
     if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
+    if (!cards || !ranks) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (flags & NPK_FLAG_VALIDATE) {
+        rc = check_rows(ds, cards, 7, nullptr, 0, nullptr, 0, 0, N, static_cast<cudaStream_t>(stream), "");
+        if (rc) return rc;
+    }
     cudaError_t e = npk::launch_rank7(ds->t, cards, N, ranks, grid_for(*ds, (N + 127) / 128, npk::kRank7Threads / 32),
                                       static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "rank7_kernel launch");
@@ -971,12 +1044,19 @@ int npk_rank7_colex(int64_t first, int64_t count, uint16_t* ranks, void* stream)
 }
 
 int npk_enum_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, uint64_t* win,
-                   uint64_t* tie, uint64_t* lose, void* stream)
+                   uint64_t* tie, uint64_t* lose, uint32_t flags, void* stream)
 {
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
     if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
+    if (!hole || !board || !n_players || !win || !tie || !lose) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (flags & NPK_FLAG_VALIDATE) {
+        rc = check_rows(ds, hole, 2, board, 5, n_players, 0, 1, Q, static_cast<cudaStream_t>(stream),
+                        " quer(ies) of a shape the enumeration does not implement (two players with 0..5 known board cards, "
+                        "or three players on a complete board)");
+        if (rc) return rc;
+    }
     npk::EnumParams p{};
     p.tables = ds->t; p.hole = hole; p.board = board; p.n_players = n_players; p.nq = Q;
     p.win = reinterpret_cast<unsigned long long*>(win);
@@ -988,13 +1068,19 @@ int npk_enum_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_p
 }
 
 int npk_showdown_batch(const uint8_t* holes, const uint8_t* n_players, const uint8_t* board, int64_t N, int maxp,
-                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, void* stream)
+                       int32_t* winner, uint8_t* wtype, uint16_t* ranks, uint32_t flags, void* stream)
 {
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
     if (N <= 0) return N == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative N");
     if (maxp < 1 || maxp > 23) return fail(NPK_ERR_INVALID_ARGUMENT, "maxp must be 1..23");
+    if (!holes || !n_players || !board || !winner || !wtype) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (flags & NPK_FLAG_VALIDATE) {
+        rc = check_rows(ds, holes, 2 * maxp, board, 5, n_players, maxp, 0, N, static_cast<cudaStream_t>(stream),
+                        " table(s) with n_players outside 1..maxp");
+        if (rc) return rc;
+    }
     cudaError_t e = npk::launch_showdown(ds->t, holes, n_players, board, N, maxp, winner, wtype, ranks,
                                          grid_for(*ds, (N + 127) / 128, npk::kRank7Threads / 32), static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? NPK_OK : cuda_fail(e, "showdown_kernel launch");

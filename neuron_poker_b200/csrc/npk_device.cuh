@@ -27,13 +27,32 @@ struct DeviceTables {
     uint32_t rowoff_bytes;
     uint32_t flush_bytes;
     uint16_t type_start[10];
+    uint32_t* check;               // one device word: highest code of a failed NPK_CHECK (checked builds), else untouched
 };
 
 struct SmemTables {
     const uint16_t* value;
     const uint16_t* rowoff;
     const uint16_t* flush;
+    const uint32_t* desc;          // [52] (+ padding to kDescBytes)
+    uint32_t value_bytes, rowoff_bytes, flush_bytes;
+    uint32_t* check;
 };
+
+// ---- checked build (-DNPK_CHECKED, tools/checked_build.sh) ------------------------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this was developed on, so the library carries its own bounds checks:
+// every shared-memory gather of the evaluator, every deck slot of the dealers and every decoded Lehmer slot is checked
+// against its bounds, and the shuffled deck is compared with the canonical one after every work item (a racing or missing
+// restore shows up there).  A failed check records its code in DeviceTables::check (npk_checked_status reads it).
+// Codes: 1 rowoff gather, 2 value gather, 3 flush gather, 4 Fisher-Yates slot, 5 Lehmer slot, 6 duplicate Lehmer slot,
+//        7 deck not restored, 8 descriptor index, 9 enumeration pair list.
+#ifdef NPK_CHECKED
+#define NPK_CHECK(ptr, cond, code) do { if (!(cond)) atomicMax((ptr), (unsigned)(code)); } while (0)
+#else
+#define NPK_CHECK(ptr, cond, code) do { } while (0)
+#endif
+
+constexpr uint32_t kDescBytes = 256;   // the 52 card descriptors follow the flush table in the device blob, padded
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,7 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 }
 
 // Stage the three lookup tables into shared memory.  Called by every thread of the CTA; returns shared pointers.
-// `base` must be 16-byte aligned; uses value_bytes + rowoff_bytes + flush_bytes bytes; `bar` is one 8-byte slot.
+// `base` must be 16-byte aligned; uses value_bytes + rowoff_bytes + flush_bytes + kDescBytes bytes; `bar` is one 8-byte slot.
 __device__ __forceinline__ SmemTables stage_tables(const DeviceTables& t, uint8_t* base, uint64_t* bar)
 {
     uint8_t* s_value = base;
@@ -76,18 +95,21 @@ __device__ __forceinline__ SmemTables stage_tables(const DeviceTables& t, uint8_
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, t.value_bytes + t.rowoff_bytes + t.flush_bytes);
+        mbar_expect_tx(bar, t.value_bytes + t.rowoff_bytes + t.flush_bytes + kDescBytes);
         const uint32_t kChunk = 32768;
         for (uint32_t o = 0; o < t.value_bytes; o += kChunk)
             bulk_g2s(s_value + o, (const uint8_t*)t.value + o, min(kChunk, t.value_bytes - o), bar);
         bulk_g2s(s_rowoff, t.rowoff, t.rowoff_bytes, bar);
         bulk_g2s(s_flush, t.flush, t.flush_bytes, bar);
+        bulk_g2s(s_flush + t.flush_bytes, t.desc, kDescBytes, bar);
     }
     mbar_wait(bar, 0);
     SmemTables s;
     s.value = (const uint16_t*)s_value;
     s.rowoff = (const uint16_t*)s_rowoff;
     s.flush = (const uint16_t*)s_flush;
+    s.desc = (const uint32_t*)(s_flush + t.flush_bytes);
+    s.value_bytes = t.value_bytes; s.rowoff_bytes = t.rowoff_bytes; s.flush_bytes = t.flush_bytes; s.check = t.check;
     return s;
 }
 
@@ -138,12 +160,19 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t saddr)
 
 struct SmemAddr {          // 32-bit shared-window addresses of the staged tables
     uint32_t value, rowoff, flush;
+#ifdef NPK_CHECKED
+    uint32_t value_bytes, rowoff_bytes, flush_bytes;
+    uint32_t* check;
+#endif
 };
 
 __device__ __forceinline__ SmemAddr smem_addr(const SmemTables& s)
 {
     SmemAddr a;
     a.value = smem_u32(s.value); a.rowoff = smem_u32(s.rowoff); a.flush = smem_u32(s.flush);
+#ifdef NPK_CHECKED
+    a.value_bytes = s.value_bytes; a.rowoff_bytes = s.rowoff_bytes; a.flush_bytes = s.flush_bytes; a.check = s.check;
+#endif
     return a;
 }
 
@@ -152,8 +181,10 @@ __device__ __forceinline__ SmemAddr smem_addr(const SmemTables& s)
 __device__ __forceinline__ uint32_t lookup_nonflush(const SmemAddr& a, uint32_t total)
 {
     const uint32_t row2 = __umulhi(total, 1u << (32 - (kDevDescShift + kRowBits - 1))) & (0xFFFFu << 1);   // 2*row
+    NPK_CHECK(a.check, row2 + 2u <= a.rowoff_bytes, 1);
     const uint32_t off = lds_u16(a.rowoff + row2);
     const uint32_t col2 = __umulhi(total, 1u << (32 - (kDevDescShift - 1))) & (kColMask << 1);              // 2*col
+    NPK_CHECK(a.check, col2 + (off << 1) + 2u <= a.value_bytes, 2);
     return lds_u16(a.value + col2 + (off << 1));
 }
 
@@ -193,6 +224,7 @@ __device__ __forceinline__ uint32_t eval7_desc(const SmemAddr& a, const uint32_t
         uint32_t field = 0;
 #pragma unroll
         for (int i = 0; i < 7; i++) field |= shr_clamp(0x1000u, (d[i] ^ fsx) & 63u);
+        NPK_CHECK(a.check, 2u * field + 2u <= a.flush_bytes, 3);
         v = lds_u16(a.flush + 2u * field);            // a flush excludes full house / quads in 7 cards
     }
     return v;

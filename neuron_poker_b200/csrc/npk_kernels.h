@@ -8,6 +8,8 @@ namespace npk {
 
 constexpr int kEquityMaxThreads = 512; // up to 16 warps per CTA, one CTA per SM (shared memory decides, see uniform_warps)
 constexpr size_t kMaxDynamicSmem = 232448;   // 227 KB opt-in limit per CTA on sm_100
+constexpr int kShapeGroups = 60;       // shapes of a mixed batch: group = opponents * 6 + known board cards
+constexpr int kMixedThreads = 480;     // persistent all-shapes kernel: 15 warps, decks sized for 50 unseen cards
 constexpr int kRefThreads = 512;       // generic range kernel
 constexpr int kAuxThreads = 512;
 constexpr int kRank7Threads = 1024;    // rank7 is latency-bound at one CTA per SM: 32 warps hide twice as much
@@ -52,13 +54,14 @@ struct EquityParams {
     const uint8_t* n_players;     // [Q]
     const int32_t* qindex;        // [nq] query ids handled by this launch, or null = 0..nq-1
     const uint32_t* group;        // device {count, offset} of this launch's shape group (sync-free mixed batches), or null:
-                                  // then nq = group[0] and qindex starts at qindex + group[64]
+                                  // then nq = group[0] and qindex starts at qindex + group[64].  The all-shapes kernel
+                                  // (npk_mixed.cu) reads all 60 groups: counts group[0..59], offsets group[64..123]
     long long nq;
     long long trials;             // trials per query in this launch
     long long trial_offset;       // first trial number (sharding a query over launches / GPUs)
     uint32_t query_offset;        // added to the query number in the Philox counter (sharding queries over GPUs)
     uint32_t seed_lo, seed_hi;
-    uint32_t chunk;               // trials per work item
+    uint32_t chunk, chunks;       // trials per work item, items per query (the last one may be shorter)
     uint32_t reference_dealer;    // 0: uniform dealing (K1), 1: the Python reference's dealer (K1')
     unsigned long long* work_counter;
     unsigned long long* wins;     // [Q] hero strictly best
@@ -97,6 +100,7 @@ struct EnumParams {
 size_t aux_smem(const DeviceTables& t);
 cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
                                   cudaStream_t s);
+cudaError_t launch_equity_mixed(const EquityParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);

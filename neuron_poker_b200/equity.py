@@ -252,7 +252,7 @@ def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, he
     set of class spellings (the hero is drawn from it every trial, `hole` may be None); ghost: None or [Q,2] uint8
     (0xFF = none).  Returns dict of int64 CUDA tensors like get_equity_batch."""
     import torch
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dev = _resolve_device(device)
     board = _as_cuda_u8(board, dev, (5,))
     n_players = _as_cuda_u8(n_players, dev, ())
     Q = board.shape[0]
@@ -260,7 +260,7 @@ def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, he
     ghost = None if ghost is None else _as_cuda_u8(ghost, dev, (2,))
     opp_mask = ranges.opponent_mask(opponent_range)
     hero_mask = None if hero_range is None else ranges.mask_from_classes(hero_range)
-    L = _lib.ensure_init(dev.index if dev.index is not None else 0)
+    L = _lib.ensure_init(dev.index)
     with torch.cuda.device(dev):
         out = {} if out is None else out
         for name, shape, want in (("wins", (Q,), True), ("ties", (Q,), True), ("win_types", (Q, 9), win_types),
@@ -281,6 +281,16 @@ def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, he
     out["trials"] = int(trials)
     return out
 
+
+
+def _resolve_device(device):
+    """torch.device with an explicit index: 'cuda' (or None) means torch's CURRENT device, not device 0 -- libnpk selects the
+    device by index, and the tensors must live where its kernels run."""
+    import torch
+    dev = torch.device("cuda") if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError("libnpk runs on CUDA devices only (there is no CPU fallback): got %r" % (device,))
+    return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
 
 
 def _as_cuda_u8(x, device, shape_tail):
@@ -309,20 +319,21 @@ def get_equity_batch(hole, board, n_players, trials, seed_value=0, deal_mode="un
     """Monte-Carlo counts for a batch of queries on the GPU (asynchronous on the current torch stream).
 
     hole [Q,2], board [Q,5] (0xFF padding), n_players [Q]: uint8 torch tensors (or array-likes, copied to the device).
-    uniform_shape=(players, known_board_cards) promises every query has that shape (no classification round trip).
-    shapes=shape_mask(...) runs a MIXED batch without any host round trip: the shapes are sorted out on the device and
-    one kernel per shape in the mask is enqueued (npk_equity_batch_async); queries of other shapes are skipped.
+    uniform_shape=(players, known_board_cards) promises every query has that shape: that shape's own kernel runs.
+    Otherwise the batch may MIX shapes: the queries are sorted by shape on the device and one persistent kernel handles all
+    of them (csrc/npk_mixed.cu) -- no host round trip unless validate=True.  shapes=shape_mask(...) restricts a mixed batch
+    to some shapes (npk_equity_batch_async); queries of other shapes are skipped.
     trial_offset / query_offset shift the Philox counters, so shards of a larger job reproduce its exact numbers.
     Returns dict of int64 CUDA tensors: wins [Q], ties [Q] (+ win_types [Q,9], passes [Q]); the counters are u64 on
     the device and viewed as int64.  `out` may hold preallocated zeroed tensors to accumulate into.
     """
     import torch
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dev = _resolve_device(device)
     hole = _as_cuda_u8(hole, dev, (2,))
     board = _as_cuda_u8(board, dev, (5,))
     n_players = _as_cuda_u8(n_players, dev, ())
     Q = hole.shape[0]
-    L = _lib.ensure_init(dev.index if dev.index is not None else 0)
+    L = _lib.ensure_init(dev.index)
     with torch.cuda.device(dev):
         out = {} if out is None else out
         for name, shape, want in (("wins", (Q,), True), ("ties", (Q,), True), ("win_types", (Q, 9), win_types),

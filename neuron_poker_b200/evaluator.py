@@ -19,21 +19,32 @@ def _torch():
 
 
 def _dev(device):
-    torch = _torch()
-    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    from .equity import _resolve_device
+    return _resolve_device(device)
 
 
-def rank7(cards, device=None):
-    """cards: [N,7] uint8 card ids (torch tensor or array-like) -> int16-viewable uint16 CUDA tensor of rank ids."""
+def _want_check(x, validate):
+    """Inputs are validated on the device (NPK_FLAG_VALIDATE: one extra pass + a synchronisation) unless the caller hands
+    over CUDA tensors -- the batched hot-path form -- and does not ask for it."""
+    if validate is None:
+        torch = _torch()
+        validate = not (isinstance(x, torch.Tensor) and x.is_cuda)
+    return _lib.NPK_FLAG_VALIDATE if validate else 0
+
+
+def rank7(cards, device=None, validate=None):
+    """cards: [N,7] uint8 card ids (torch tensor or array-like) -> int16-viewable uint16 CUDA tensor of rank ids.
+    validate: check ids / duplicates first (ValueError-like NpkError); default: yes unless `cards` is a CUDA tensor."""
     torch = _torch()
     dev = _dev(device)
+    flags = _want_check(cards, validate)
     if not isinstance(cards, torch.Tensor):
         cards = torch.as_tensor(np.ascontiguousarray(cards, dtype=np.uint8))
     cards = cards.to(dev).contiguous().view(-1, 7)
-    L = _lib.ensure_init(dev.index or 0)
+    L = _lib.ensure_init(dev.index)
     out = torch.empty(cards.shape[0], dtype=torch.uint16, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.npk_rank7_batch(cards.data_ptr(), cards.shape[0], out.data_ptr(),
+        _lib.check(L.npk_rank7_batch(cards.data_ptr(), cards.shape[0], out.data_ptr(), flags,
                                      torch.cuda.current_stream(dev).cuda_stream))
     return out
 
@@ -42,30 +53,31 @@ def rank7_colex(first, count, device=None):
     """rank ids of hands number first..first+count-1 of the colexicographic enumeration of all C(52,7) hands."""
     torch = _torch()
     dev = _dev(device)
-    L = _lib.ensure_init(dev.index or 0)
+    L = _lib.ensure_init(dev.index)
     out = torch.empty(int(count), dtype=torch.uint16, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.npk_rank7_colex(int(first), int(count), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
     return out
 
 
-def showdown(holes, n_players, board, device=None, return_ranks=False):
+def showdown(holes, n_players, board, device=None, return_ranks=False, validate=None):
     """Batched get_winner: holes [N,maxp,2], n_players [N], board [N,5] -> (winner int32 [N], type uint8 [N][, ranks])."""
     torch = _torch()
     dev = _dev(device)
+    flags = _want_check(holes, validate)
     holes = torch.as_tensor(np.ascontiguousarray(holes, dtype=np.uint8)) if not isinstance(holes, torch.Tensor) else holes
     board = torch.as_tensor(np.ascontiguousarray(board, dtype=np.uint8)) if not isinstance(board, torch.Tensor) else board
     n_players = torch.as_tensor(np.ascontiguousarray(n_players, dtype=np.uint8)) if not isinstance(n_players, torch.Tensor) else n_players
     holes, board, n_players = holes.to(dev).contiguous(), board.to(dev).contiguous(), n_players.to(dev).contiguous()
     N, maxp = holes.shape[0], holes.shape[1]
-    L = _lib.ensure_init(dev.index or 0)
+    L = _lib.ensure_init(dev.index)
     winner = torch.empty(N, dtype=torch.int32, device=dev)
     wtype = torch.empty(N, dtype=torch.uint8, device=dev)
     ranks = torch.zeros((N, maxp), dtype=torch.uint16, device=dev) if return_ranks else None
     with torch.cuda.device(dev):
         _lib.check(L.npk_showdown_batch(holes.data_ptr(), n_players.data_ptr(), board.data_ptr(), N, maxp,
                                         winner.data_ptr(), wtype.data_ptr(), ranks.data_ptr() if return_ranks else None,
-                                        torch.cuda.current_stream(dev).cuda_stream))
+                                        flags, torch.cuda.current_stream(dev).cuda_stream))
     return (winner, wtype, ranks) if return_ranks else (winner, wtype)
 
 
@@ -93,11 +105,12 @@ def eval_best_hand(hands):
     return hands[best], HAND_TYPES[ty]
 
 
-def enumerate_equity(hole, board, n_players=None, device=None):
+def enumerate_equity(hole, board, n_players=None, device=None, validate=None):
     """Exact enumeration (no sampling): hole [Q,2], board [Q,5] with 0xFF padding, n_players [Q] (2, or 3 on a complete
     board).  Returns int64 CUDA tensors (win, tie, lose) of hero-strictly-best / tied / beaten counts."""
     torch = _torch()
     dev = _dev(device)
+    flags = _want_check(hole, validate)
     hole = torch.as_tensor(np.ascontiguousarray(hole, dtype=np.uint8)) if not isinstance(hole, torch.Tensor) else hole
     board = torch.as_tensor(np.ascontiguousarray(board, dtype=np.uint8)) if not isinstance(board, torch.Tensor) else board
     hole, board = hole.to(dev).contiguous().view(-1, 2), board.to(dev).contiguous().view(-1, 5)
@@ -107,13 +120,13 @@ def enumerate_equity(hole, board, n_players=None, device=None):
     elif not isinstance(n_players, torch.Tensor):
         n_players = torch.as_tensor(np.ascontiguousarray(n_players, dtype=np.uint8))
     n_players = n_players.to(dev).contiguous()
-    L = _lib.ensure_init(dev.index or 0)
+    L = _lib.ensure_init(dev.index)
     win = torch.zeros(Q, dtype=torch.int64, device=dev)
     tie = torch.zeros(Q, dtype=torch.int64, device=dev)
     lose = torch.zeros(Q, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.npk_enum_batch(hole.data_ptr(), board.data_ptr(), n_players.data_ptr(), Q, win.data_ptr(),
-                                    tie.data_ptr(), lose.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+                                    tie.data_ptr(), lose.data_ptr(), flags, torch.cuda.current_stream(dev).cuda_stream))
     return win, tie, lose
 
 

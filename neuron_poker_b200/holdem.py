@@ -121,8 +121,9 @@ class HoldemTables(object):
                  max_raises_per_player_round=2, autoplay=None, seed=0, table_offset=0, device=None):
         import torch
         self.torch = torch
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.L = _bind(_lib.ensure_init(self.device.index if self.device.index is not None else 0))
+        from .equity import _resolve_device
+        self.device = _resolve_device(device)
+        self.L = _bind(_lib.ensure_init(self.device.index))
         self.n_tables, self.n_players = int(n_tables), int(n_players)
         self.seed, self.table_offset = int(seed), int(table_offset)
         self.params = (float(initial_stacks), float(small_blind), float(big_blind), int(max_raises_per_player_round))
@@ -204,26 +205,27 @@ class HoldemTables(object):
         self.decisions += 1
         return actions
 
-    def selfplay_step(self, agents, runs=1000, deal_mode="reference", restart_finished=True, sync_free=False):
+    # kernels of libnpk per self-play step: holdem_queries, classify_count, classify_fill, equity_mixed, holdem_decide,
+    # holdem_step (+ one memset of the workspace header and one torch zero_ of the [2,N] counters)
+    launches_per_step = 6
+
+    def selfplay_step(self, agents, runs=1000, deal_mode="reference", restart_finished=True, sync_free=True):
         """One action on every table, entirely on the device: the equity query of every current player
-        (env.py:262-264: 1,000 runs, all players alive), the Monte-Carlo kernels, the agents' decisions
+        (env.py:262-264: 1,000 runs, all players alive), the Monte-Carlo kernel, the agents' decisions
         (agent_consider_equity / random) and the state machine.  Returns the actions taken (int8 CUDA tensor).
-        sync_free=True sorts the queries by shape on the device and enqueues a kernel for every shape a table can ask
-        for (no host round trip at all: the step can be captured in a CUDA graph); the default reads the shape counts
-        back once per step and launches only the shapes present, side by side, which is faster (1.5 vs 2.1 ms for 65,536
-        tables on a B200)."""
-        from .equity import get_equity_batch, shape_mask
+        The queries of a step mix player counts and streets: they are sorted by shape on the device and ONE persistent
+        kernel handles all shapes (csrc/npk_mixed.cu); nothing is read back, so the step can be captured in a CUDA graph.
+        (`sync_free` is accepted for compatibility: every mixed batch is free of host round trips now.)"""
+        from .equity import get_equity_batch
         hole, board, npl, _ = self.queries()
         out = getattr(self, "_mc_out", None)
         if out is None:
-            out = {"wins": self.torch.zeros(self.n_tables, dtype=self.torch.int64, device=self.device),
-                   "ties": self.torch.zeros(self.n_tables, dtype=self.torch.int64, device=self.device)}
+            both = self.torch.zeros((2, self.n_tables), dtype=self.torch.int64, device=self.device)
+            out = {"wins": both[0], "ties": both[1], "_both": both}
             self._mc_out = out
-        out["wins"].zero_(); out["ties"].zero_()
-        # sync_free: the shapes a table can ask for are 1 (inactive tables) .. n_players players, 0 / 3 / 4 / 5 board cards
+        out["_both"].zero_()
         get_equity_batch(hole, board, npl, runs, seed_value=(self.seed << 20) + self.decisions, deal_mode=deal_mode,
-                         query_offset=self.table_offset, validate=False, out=out, device=self.device,
-                         shapes=shape_mask(range(1, self.n_players + 1)) if sync_free else None)
+                         query_offset=self.table_offset, validate=False, out=out, device=self.device)
         actions = self.decide(agents, wins=out["wins"], ties=out["ties"], runs=runs)
         self.step(actions, restart_finished=restart_finished)
         return actions

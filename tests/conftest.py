@@ -57,3 +57,22 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def checked_build_reports_no_failure():
+    """When the suite runs against the checked build of the library (NPK_LIBRARY=.../libnpk_checked.so, see
+    tools/checked_build.sh: the stand-in for compute-sanitizer), no bounds / deck-restore check may have failed."""
+    yield
+    if not os.environ.get("NPK_LIBRARY"):
+        return
+    import ctypes
+    import torch
+    if not torch.cuda.is_available():
+        return
+    from neuron_poker_b200 import _lib
+    L = _lib.ensure_init(0)
+    checked, code = ctypes.c_int(0), ctypes.c_uint32(0)
+    _lib.check(L.npk_checked_status(ctypes.byref(checked), ctypes.byref(code)))
+    print("\nchecked build: %d, first failed check: %d" % (checked.value, code.value))
+    assert code.value == 0, "NPK_CHECK code %d failed (csrc/npk_device.cuh)" % code.value

@@ -381,6 +381,73 @@ def test_invalid_queries_are_reported(torch_mod):
     assert out["wins"].shape == (0,)
 
 
+def test_evaluator_entry_points_validate_their_inputs(torch_mod):
+    """npk_rank7_batch / npk_showdown_batch / npk_enum_batch with NPK_FLAG_VALIDATE (the default for host arrays): a card id
+    >= 52 -- including the 0xFF pad -- a duplicate card, n_players out of range or an enumeration shape the kernel does not
+    implement is an error, not an out-of-bounds gather (the reference raises ValueError / RuntimeError there).  Without the
+    flag the call is the caller's responsibility but must stay memory-safe."""
+    torch = torch_mod
+    good = np.array([[0, 5, 9, 13, 22, 37, 51]], dtype=np.uint8)
+    assert int(npk.rank7(good)[0]) == int(npk.host_rank7(good)[0])
+    for bad in ([[0, 5, 9, 13, 22, 37, 52]], [[0, 5, 9, 13, 22, 37, 255]], [[0, 5, 9, 13, 22, 37, 37]]):
+        with pytest.raises(_lib.NpkError) as e:
+            npk.rank7(np.array(bad, dtype=np.uint8))
+        assert e.value.code == -5
+    junk = torch.randint(0, 256, (4096, 7), dtype=torch.uint8, device="cuda")
+    npk.rank7(junk, validate=False)                      # garbage in, garbage out -- but no fault
+    torch.cuda.synchronize()
+    hole, board = np.array([[0, 1]], dtype=np.uint8), np.array([[2, 3, 4, 5, 6]], dtype=np.uint8)
+    with pytest.raises(_lib.NpkError) as e:
+        npk.enumerate_equity(hole, board, np.array([4], dtype=np.uint8))          # four players: not implemented
+    assert e.value.code == -2
+    with pytest.raises(_lib.NpkError) as e:
+        npk.enumerate_equity(hole, np.array([[2, 3, 4, NO, NO]], dtype=np.uint8), np.array([3], dtype=np.uint8))
+    assert e.value.code == -2
+    with pytest.raises(_lib.NpkError) as e:
+        npk.enumerate_equity(np.array([[0, 60]], dtype=np.uint8), board)
+    assert e.value.code == -5
+    with pytest.raises(_lib.NpkError) as e:
+        npk.enumerate_equity(hole, np.array([[2, NO, 4, NO, NO]], dtype=np.uint8))  # gap in the board
+    assert e.value.code == -5
+    w, t, l = npk.enumerate_equity(torch.randint(0, 256, (64, 2), dtype=torch.uint8, device="cuda"),
+                                   torch.randint(0, 256, (64, 5), dtype=torch.uint8, device="cuda"), validate=False)
+    torch.cuda.synchronize()
+    holes = np.array([[[0, 1], [2, 3], [255, 255]]], dtype=np.uint8)
+    brd = np.array([[10, 20, 30, 40, 50]], dtype=np.uint8)
+    npk.showdown(holes, np.array([2], dtype=np.uint8), brd)                       # unused third seat may hold anything
+    with pytest.raises(_lib.NpkError) as e:
+        npk.showdown(holes, np.array([3], dtype=np.uint8), brd)
+    assert e.value.code == -5
+    with pytest.raises(_lib.NpkError) as e:
+        npk.showdown(holes, np.array([4], dtype=np.uint8), brd)
+    assert e.value.code == -2
+    with pytest.raises(_lib.NpkError):
+        npk.showdown(np.array([[[0, 1], [1, 3], [4, 5]]], dtype=np.uint8), np.array([2], dtype=np.uint8), brd)
+
+
+def test_mixed_batch_status_reports_skipped_and_invalid_queries(torch_mod):
+    """npk_equity_batch_async validates nothing by itself; npk_equity_batch_status tells afterwards how many queries of the
+    last call were invalid or outside the shape mask (their counters are untouched)."""
+    import ctypes
+    torch = torch_mod
+    hole = torch.tensor([[0, 1], [2, 3], [4, 4], [6, 7]], dtype=torch.uint8, device="cuda")
+    board = torch.full((4, 5), NO, dtype=torch.uint8, device="cuda")
+    npl = torch.tensor([2, 3, 2, 2], dtype=torch.uint8, device="cuda")
+    L = _lib.ensure_init(0)
+    ws = torch.empty(int(L.npk_equity_workspace_bytes(4)), dtype=torch.uint8, device="cuda")
+    wins = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ties = torch.zeros(4, dtype=torch.int64, device="cuda")
+    mask = npk.equity.shape_mask([2], [0])
+    _lib.check(L.npk_equity_batch_async(hole.data_ptr(), board.data_ptr(), npl.data_ptr(), 4, 500, ctypes.c_uint64(mask),
+                                        ctypes.c_uint64(5), 0, 0, 0, wins.data_ptr(), ties.data_ptr(), None, None,
+                                        ws.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    inv, skp = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    _lib.check(L.npk_equity_batch_status(ws.data_ptr(), torch.cuda.current_stream().cuda_stream, ctypes.byref(inv), ctypes.byref(skp)))
+    assert (inv.value, skp.value) == (1, 1)
+    tot = (wins + ties).cpu().tolist()
+    assert tot[0] > 0 and tot[3] > 0 and tot[1] == 0 and tot[2] == 0
+
+
 def test_one_query_fast_path_equals_the_batched_path(torch_mod):
     """npk_equity_host with one query takes a copy-free path (query in the kernel parameters, counters resident on the
     device and reset by the last warp, results in mapped host memory).  Same seed, same query => the same counters as

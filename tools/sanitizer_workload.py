@@ -1,6 +1,9 @@
 """Every kernel of libnpk once, at sizes compute-sanitizer finishes in minutes (racecheck / memcheck / synccheck
 on the shared-memory staging, the per-warp decks and the reductions).  Run as
     compute-sanitizer --tool memcheck|racecheck|synccheck|initcheck python tools/sanitizer_workload.py
+or, where compute-sanitizer is not available (it is closed on the pool this was built on, profiles/r02_compute_sanitizer_closed.txt),
+against the library's own checked build:
+    bash tools/checked_build.sh && NPK_LIBRARY=$PWD/neuron_poker_b200/build/libnpk_checked.so python tools/sanitizer_workload.py
 The results are checked for self-consistency only (wins + ties <= trials, enumeration totals); parity is tests/'s job."""
 import os
 import sys
@@ -99,4 +102,11 @@ torch.cuda.synchronize()
 st = tb.state()
 assert int((st["error"] != 0).sum()) == 0
 print("ok holdem self-play", flush=True)
+import ctypes
+from neuron_poker_b200 import _lib
+L = _lib.ensure_init(0)
+checked, code = ctypes.c_int(0), ctypes.c_uint32(0)
+_lib.check(L.npk_checked_status(ctypes.byref(checked), ctypes.byref(code)))
+print("checked build: %d   first failed NPK_CHECK: %d" % (checked.value, code.value))
+assert code.value == 0
 print("sanitizer workload finished")
