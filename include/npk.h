@@ -143,6 +143,13 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
                     uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                     uint64_t* passes);
 
+/* HOST, blocking: ONE query with as few arguments as a foreign-function call can have -- what the Python drop-in's get_equity
+ * (montecarlo_python.py:401-406) calls.  packed = hole[0] | hole[1] << 8 | board[0] << 16 | ... | board[4] << 48 (card ids,
+ * 0xFF = no card, known cards first); want bit 0: win types, bit 1: passes; out[12] (host) = wins, ties, win types[9],
+ * passes.  One kernel launch, no copies, no stream synchronisation (the kernel publishes the result and the call's
+ * sequence number in mapped host memory; the host spins on the number).  Validated like npk_equity_host. */
+int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, int deal_mode, uint32_t want, uint64_t* out);
+
 /*
  * Monte-Carlo equity with RANGES (run_montecarlo's opponent_range / set-typed player cards / ghost_cards).
  * A starting-hand class is an unordered rank pair plus suitedness, numbered  suited hi*13+lo,  offsuit and pairs

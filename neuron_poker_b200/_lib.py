@@ -50,6 +50,7 @@ def lib():
                                                      u64, u64, u64, u64, vp, vp]
                 L.npk_equity_batch_status.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
                 L.npk_equity_host.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, i32, u64, u64, u64, u64]
+                L.npk_equity_one.argtypes = [ctypes.c_uint64, i32, i64, ctypes.c_uint64, i32, ctypes.c_uint32, u64]
                 L.npk_equity_ranges_batch.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i64, i64, i32,
                                                       ctypes.c_uint32, u64, u64, u64, u64, vp, vp]
                 L.npk_equity_ranges_host.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i32, u64, u64,
@@ -84,10 +85,24 @@ def init(device=0):
     return L
 
 
+_current = threading.local()
+
+
 def ensure_init(device=0):
     """Initialise `device` on first use and make it current for this thread inside libnpk's CUDA runtime."""
-    if int(device) not in _inited:
-        return init(device)
-    L = lib()
-    check(L.npk_set_device(int(device)))
+    device = int(device)
+    if device not in _inited:
+        L = init(device)
+    else:
+        L = lib()
+        check(L.npk_set_device(device))
+    _current.device = device
     return L
+
+
+def ensure_current(device):
+    """ensure_init for callers that never switch devices behind libnpk's back (the one-query drop-in path): the
+    cudaSetDevice round trip is skipped when this thread's last libnpk call already selected `device`."""
+    if getattr(_current, "device", None) == device:
+        return _lib
+    return ensure_init(device)

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ struct HostStage {
     // one-query blocking calls (Q == 1): counters in device memory, results in mapped host memory
     npk::SingleCall* single = nullptr;
     npk::SingleResult* single_host = nullptr;
+    unsigned long long single_seq = 0;
     void release()
     {
         if (device < 0) return;
@@ -533,6 +535,86 @@ int npk_equity_batch_status(const void* workspace, void* stream, uint32_t* inval
     return NPK_OK;
 }
 
+namespace {
+// One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in device memory
+// between calls (the last warp hands them over and zeroes them), the result lands in mapped host memory together with the
+// call's sequence number, and the host spins on that number instead of asking the driver to synchronise the stream.
+// No H2D / D2H copy, no memset, no cudaStreamSynchronize on the fast path.
+int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, int players, int64_t trials,
+                 uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+{
+    cudaError_t e;
+    unsigned long long mask = 0;
+    int known = 0;
+    bool ended = false, bad = players < 1 || players > 10;
+    for (int i = 0; i < 2 && !bad; i++) {
+        const int c = hole[i];
+        if (c >= 52 || (mask >> c & 1ull)) bad = true; else mask |= 1ull << c;
+    }
+    for (int i = 0; i < 5 && !bad; i++) {
+        const int c = board[i];
+        if (c == 0xFF) { ended = true; continue; }
+        if (ended || c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
+        mask |= 1ull << c;
+        known++;
+    }
+    if (bad) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+    if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
+    if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (!st.single) {
+        if ((e = cudaHostAlloc(&st.single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+        std::memset(st.single_host, 0, sizeof(npk::SingleResult));
+        npk::SingleResult* dptr = nullptr;
+        if ((e = cudaHostGetDevicePointer(&dptr, st.single_host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        if ((e = cudaMalloc(&st.single, sizeof(npk::SingleCall))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        npk::SingleCall init{};
+        init.host = dptr;
+        if ((e = cudaMemcpy(st.single, &init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
+        st.single_seq = 0;
+    }
+    wins_strict[0] = 0; ties[0] = 0;
+    if (win_types) std::memset(win_types, 0, 72);
+    if (passes) passes[0] = 0;
+    if (trials == 0) return NPK_OK;
+    npk::EquityParams p{};
+    p.tables = ds->t;
+    p.hole = nullptr; p.board = nullptr; p.n_players = nullptr; p.qindex = nullptr;
+    p.inline_query = (uint64_t)hole[0] | (uint64_t)hole[1] << 8;
+    for (int i = 0; i < 5; i++) p.inline_query |= (uint64_t)board[i] << (16 + 8 * i);
+    p.nq = 1; p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    const long long chunks = plan_items(p, 1, trials, ds->sm_count);
+    p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
+    p.single = st.single;
+    p.single_seq = ++st.single_seq;
+    p.work_counter = &st.single->work_counter;
+    p.wins = &st.single->wins; p.ties = &st.single->ties;
+    p.win_types = win_types ? st.single->win_types : nullptr;
+    p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &st.single->passes : nullptr;
+    p.abort_flag = st.single->abort_flag;
+    e = npk::launch_equity_uniform(players - 1, 5 - known, p, chunks, ds->sm_count, tuning().warps, st.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
+    const volatile npk::SingleResult* r = st.single_host;
+    bool arrived = false;
+    for (long spins = 0; spins < 4000000; spins++) {              // a few hundred ms at most, then ask the driver
+        if (r->seq == p.single_seq) { arrived = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!arrived) {
+        if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
+        if (r->seq != p.single_seq) return fail(NPK_ERR_CUDA, "the one-query kernel finished without publishing its result");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    wins_strict[0] = r->wins; ties[0] = r->ties;
+    if (win_types) for (int i = 0; i < 9; i++) win_types[i] = r->win_types[i];
+    if (passes) passes[0] = r->passes;
+    return NPK_OK;
+}
+}  // namespace
+
 int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
                     uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                     uint64_t* passes)
@@ -551,66 +633,8 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
         if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
         st.device = dev;
     }
-    if (Q == 1 && !tuning().no_single_path) {
-        // One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in
-        // device memory between calls (the last warp hands them over and zeroes them), the result lands in mapped host
-        // memory.  No H2D / D2H copy, no memset.
-        unsigned long long mask = 0;
-        int known = 0;
-        bool ended = false, bad = n_players[0] < 1 || n_players[0] > 10;
-        for (int i = 0; i < 2 && !bad; i++) {
-            const int c = hole[i];
-            if (c >= 52 || (mask >> c & 1ull)) bad = true; else mask |= 1ull << c;
-        }
-        for (int i = 0; i < 5 && !bad; i++) {
-            const int c = board[i];
-            if (c == 0xFF) { ended = true; continue; }
-            if (ended || c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
-            mask |= 1ull << c;
-            known++;
-        }
-        if (bad) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
-        if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
-            return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
-        if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
-        if (!st.single) {
-            if ((e = cudaHostAlloc(&st.single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
-            npk::SingleResult* dptr = nullptr;
-            if ((e = cudaHostGetDevicePointer(&dptr, st.single_host, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
-            if ((e = cudaMalloc(&st.single, sizeof(npk::SingleCall))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-            npk::SingleCall init{};
-            init.host = dptr;
-            if ((e = cudaMemcpy(st.single, &init, sizeof init, cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "cudaMemcpy");
-        }
-        wins_strict[0] = 0; ties[0] = 0;
-        if (win_types) std::memset(win_types, 0, 72);
-        if (passes) passes[0] = 0;
-        if (trials == 0) return NPK_OK;
-        npk::EquityParams p{};
-        p.tables = ds->t;
-        p.hole = nullptr; p.board = nullptr; p.n_players = nullptr; p.qindex = nullptr;
-        p.inline_query = (uint64_t)hole[0] | (uint64_t)hole[1] << 8;
-        for (int i = 0; i < 5; i++) p.inline_query |= (uint64_t)board[i] << (16 + 8 * i);
-        p.nq = 1; p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
-        p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
-        const long long chunks = plan_items(p, 1, trials, ds->sm_count);
-        p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
-        p.single = st.single;
-        p.work_counter = &st.single->work_counter;
-        p.wins = &st.single->wins; p.ties = &st.single->ties;
-        p.win_types = win_types ? st.single->win_types : nullptr;
-        p.passes = (passes && deal_mode == NPK_DEAL_REFERENCE) ? &st.single->passes : nullptr;
-        p.abort_flag = st.single->abort_flag;
-        const int forced_warps = tuning().warps;
-        e = npk::launch_equity_uniform(n_players[0] - 1, 5 - known, p, chunks, ds->sm_count, forced_warps, st.stream);
-        if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
-        if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
-        const npk::SingleResult* r = st.single_host;
-        wins_strict[0] = r->wins; ties[0] = r->ties;
-        if (win_types) for (int i = 0; i < 9; i++) win_types[i] = r->win_types[i];
-        if (passes) passes[0] = r->passes;
-        return NPK_OK;
-    }
+    if (Q == 1 && !tuning().no_single_path)
+        return single_query(ds, st, hole, board, n_players[0], trials, seed, deal_mode, wins_strict, ties, win_types, passes);
     if (st.cap_q < Q) {
         cudaFreeHost(st.h_in); cudaFreeHost(st.h_out); cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_ws);
         st.h_in = nullptr; st.h_out = nullptr; st.d_in = nullptr; st.d_out = nullptr; st.d_ws = nullptr; st.cap_q = 0;
@@ -668,6 +692,33 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
     if (win_types) std::memcpy(win_types, st.h_out + 2 * Q, 8 * 9 * Q);
     if (passes) std::memcpy(passes, st.h_out + 11 * Q, 8 * Q);
     return NPK_OK;
+}
+
+/* One query from the host with as few arguments as a foreign-function call can have (the Python drop-in's get_equity):
+ * packed = hole[0] | hole[1] << 8 | board[0..4] << 16.. (bytes, 0xFF = no card); out[12] = wins, ties, win types[9], passes. */
+int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, int deal_mode, uint32_t want, uint64_t* out)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (!out) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    uint8_t q[7];
+    for (int i = 0; i < 7; i++) q[i] = (uint8_t)(packed >> (8 * i));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    HostStage& st = t_stage;
+    if (st.device != dev) st.release();
+    if (st.device < 0) {
+        cudaError_t e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "stream");
+        st.device = dev;
+    }
+    const uint8_t np = (uint8_t)(players < 0 || players > 255 ? 255 : players);
+    if (tuning().no_single_path)
+        return npk_equity_host(q, q + 2, &np, 1, trials, seed, deal_mode, out, out + 1, (want & 1u) ? out + 2 : nullptr,
+                               (want & 2u) ? out + 11 : nullptr);
+    return single_query(ds, st, q, q + 2, players, trials, seed, deal_mode, out, out + 1, (want & 1u) ? out + 2 : nullptr,
+                        (want & 2u) ? out + 11 : nullptr);
 }
 
 // ---- trial-sharded jobs: count reduction over NVLink peer memory inside the kernel -----------------------------------------

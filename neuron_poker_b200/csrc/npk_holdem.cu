@@ -497,8 +497,24 @@ __global__ void __launch_bounds__(kStepThreads) holdem_step_kernel(T* tables, lo
     constexpr int kWordsPerTable = (int)(sizeof(T) / 8);
     const unsigned long long* g_words = reinterpret_cast<const unsigned long long*>(tables + first);
     const int total_words = (int)count * kWordsPerTable;
-    for (int w = threadIdx.x; w < total_words; w += kStepThreads) s_words[w] = g_words[w];
-    __syncthreads();
+    // the block's tables travel as ONE bulk copy each way (cp.async.bulk, the TMA 1-D path): 45 KB in a single instruction
+    // instead of 89 dependent 8-byte loads per thread -- the first version of this kernel spent its time waiting for them
+    // (98 us per step for 65,536 tables, long-scoreboard stalls 46 %, profiles/r02_ncu_holdem_step.txt)
+    __shared__ uint64_t s_bar;
+    const uint32_t bytes = (uint32_t)total_words * 8u;
+    const bool bulk = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(g_words) & 15u) == 0;
+    if (bulk) {
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_words, g_words, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int w = threadIdx.x; w < total_words; w += kStepThreads) s_words[w] = g_words[w];
+        __syncthreads();
+    }
     const long long i = first + threadIdx.x;
     bool touched = false;
     if (threadIdx.x < count) {
@@ -513,7 +529,18 @@ __global__ void __launch_bounds__(kStepThreads) holdem_step_kernel(T* tables, lo
     // write back only if some table of the block was stepped
     if (!__syncthreads_or(touched)) return;
     unsigned long long* o_words = reinterpret_cast<unsigned long long*>(tables + first);
-    for (int w = threadIdx.x; w < total_words; w += kStepThreads) o_words[w] = s_words[w];
+    if (bulk) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the threads' shared-memory writes -> the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o_words), "r"(smem_u32(s_words)), "r"(bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the read
+        }
+    } else {
+        for (int w = threadIdx.x; w < total_words; w += kStepThreads) o_words[w] = s_words[w];
+    }
 }
 
 // Attach the StageData array.  The first hand has already been dealt by init, so the blinds it posted are replayed into

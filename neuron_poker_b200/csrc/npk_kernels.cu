@@ -224,25 +224,59 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
 // =====================================================================================================================
 // Four consecutive hands per thread: their 28 bytes are seven aligned 32-bit words (a warp reads 896 contiguous bytes),
 // all seven loads are issued before the first use, and the four rank ids leave as one 8-byte store.  HBM traffic is the
-// algorithmic 9 B per hand; the per-card work is one byte extract, one descriptor gather from shared memory, one add into
-// the key sum and the suit-counter update.
+// algorithmic 9 B per hand.  Round 1's kernel was bound by the alu pipe (87 %) and by shared-memory wavefronts (28 per 32
+// hands in 33 SM cycles): per card a byte extract, a gather from a 52-word descriptor table (about 3 wavefronts, random
+// banks), an add into the key sum and three instructions to turn the suit into a counter increment
+// (profiles/r02_ncu_rank7_before.txt).  Now the card table holds {descriptor, suit-counter increment} as 8-byte entries,
+// replicated per lane ([64 cards][32 lanes], 16 KB): one conflict-free LDS.64 per card (2 wavefronts, the minimum for
+// 256 B), no suit arithmetic, and the byte extract is one mask (alu) plus one multiply-high that shifts the id into the
+// address and adds the lane's base (fma pipe, idle in this kernel).
 __global__ void __launch_bounds__(kRank7Threads, 1) rank7_kernel(const DeviceTables tables, const uint8_t* __restrict__ cards,
                                                                long long n, uint16_t* __restrict__ out)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     const SmemAddr st = smem_addr(stage_tables(tables, smem + 128, bar));
-    // per-card descriptor table in shared memory (a 13-word per-rank table would be conflict-free, but rebuilding the
-    // descriptor from rank and suit costs three more alu instructions per card, and this kernel is alu-bound: measured)
-    uint32_t* s_desc = reinterpret_cast<uint32_t*>(smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes);
-    if (threadIdx.x < 64) s_desc[threadIdx.x] = threadIdx.x < 52 ? tables.desc[threadIdx.x] : 0u;
+    uint8_t* extra = smem + 128 + tables.value_bytes + tables.rowoff_bytes + tables.flush_bytes + kDescBytes;
+    uint2* s_card = reinterpret_cast<uint2*>(extra);                  // [64][32] {descriptor, 1 << 4*suit}; ids 52..63 -> {0, 0}
+    for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+        const int c = i >> 5;
+        const uint32_t d = c < 52 ? tables.desc[c] : 0u;
+        s_card[i] = make_uint2(d, c < 52 ? suit_inc(d) : 0u);
+    }
     __syncthreads();
-    auto card_desc = [&](uint32_t card) { return s_desc[card & 63u]; };     // 64 slots: never out of bounds (ids >= 52 are the caller's
-                                                                            // error, reported by NPK_FLAG_VALIDATE; they rank as garbage)
+    const uint32_t lane_base = smem_u32(s_card) + 8u * (threadIdx.x & 31);
+    // entry of the card in byte k of word w (id clamped to 64 slots: an id >= 52 is the caller's error, reported by
+    // NPK_FLAG_VALIDATE, and ranks as garbage, never out of bounds): shared address = lane_base + id * 256
+    auto card_entry = [&](uint32_t w, int k) {
+        const uint32_t f = w & (0x3Fu << (8 * k));
+        uint32_t addr;
+        if (k == 0) addr = f * 256u + lane_base;
+        else if (k == 1) addr = f + lane_base;
+        else asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(f), "r"(1u << (32 - (8 * k - 8))), "r"(lane_base));
+        uint2 e;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr));
+        return e;
+    };
+    auto eval7 = [&](const uint2 (&e)[7]) {
+        const uint32_t total = (e[0].x + e[1].x + e[2].x) + (e[3].x + e[4].x + e[5].x) + e[6].x;
+        const uint32_t cnt = (0x3333u + e[0].y + e[1].y) + (e[2].y + e[3].y + e[4].y) + (e[5].y + e[6].y);
+        uint32_t v = lookup_nonflush(st, total);
+        const uint32_t f = cnt & 0x8888u;                 // nibble >= 8  <=>  that suit holds >= 5 cards
+        if (f) {
+            const uint32_t fsx = (((31u - __clz(f)) >> 2) & 3u) << 4;
+            uint32_t field = 0;
+#pragma unroll
+            for (int i = 0; i < 7; i++) field |= shr_clamp(0x1000u, (e[i].x ^ fsx) & 63u);
+            NPK_CHECK(st.check, 2u * field + 2u <= st.flush_bytes, 3);
+            v = lds_u16(st.flush + 2u * field);           // a flush excludes full house / quads in 7 cards
+        }
+        return v;
+    };
     const bool aligned = ((reinterpret_cast<uintptr_t>(cards) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7u) == 0);
     const long long quads = aligned ? n / 4 : 0;
     const uint32_t* __restrict__ words = reinterpret_cast<const uint32_t*>(cards);
-    // software pipeline: the seven words of the NEXT quad are in flight while this one is evaluated (one CTA of 16 warps
+    // software pipeline: the seven words of the NEXT quad are in flight while this one is evaluated (one CTA of 32 warps
     // per SM cannot hide HBM latency by occupancy alone)
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,13 +296,13 @@ __global__ void __launch_bounds__(kRank7Threads, 1) rank7_kernel(const DeviceTab
         uint32_t r[4];
 #pragma unroll
         for (int h = 0; h < 4; h++) {
-            uint32_t d[7];
+            uint2 e[7];
 #pragma unroll
             for (int k = 0; k < 7; k++) {
                 const int byte = 7 * h + k;
-                d[k] = card_desc((w[byte >> 2] >> (8 * (byte & 3))) & 0xFFu);
+                e[k] = card_entry(w[byte >> 2], byte & 3);
             }
-            r[h] = eval7_desc(st, d);
+            r[h] = eval7(e);
         }
         uint2 packed;
         packed.x = r[0] | (r[1] << 16);
@@ -276,10 +310,10 @@ __global__ void __launch_bounds__(kRank7Threads, 1) rank7_kernel(const DeviceTab
         *reinterpret_cast<uint2*>(out + 4 * g) = packed;
     }
     for (long long i = 4 * quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        uint32_t d[7];
+        uint2 e[7];
 #pragma unroll
-        for (int k = 0; k < 7; k++) d[k] = card_desc(cards[7 * i + k]);
-        out[i] = (uint16_t)eval7_desc(st, d);
+        for (int k = 0; k < 7; k++) e[k] = card_entry(cards[7 * i + k], 0);
+        out[i] = (uint16_t)eval7(e);
     }
 }
 
@@ -630,7 +664,7 @@ cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid,
 
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s)
 {
-    size_t smem = aux_smem(t);
+    size_t smem = 128 + t.value_bytes + t.rowoff_bytes + t.flush_bytes + kDescBytes + 64 * 32 * 8;   // + the per-lane card table
     cudaError_t e = cudaFuncSetAttribute(rank7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     rank7_kernel<<<grid, kRank7Threads, smem, s>>>(t, cards, n, out);

@@ -19,6 +19,7 @@ constexpr int kRank7Threads = 1024;    // rank7 is latency-bound at one CTA per 
 // next call, and publishes `done`.
 struct SingleResult {             // in mapped host memory
     unsigned long long wins, ties, win_types[9], passes;
+    unsigned long long seq;       // number of the call these values belong to: written last, the host spins on it
 };
 struct SingleCall {               // in device memory
     unsigned long long wins, ties, win_types[9], passes;
@@ -71,6 +72,7 @@ struct EquityParams {
     // ---- single blocking call (npk_equity_host with one query): no copies, no memsets ----
     uint64_t inline_query;        // hole[2] | board[5] << 16 (bytes), used when `hole` is null
     SingleCall* single;           // device scratch + mapped host result block, or null
+    unsigned long long single_seq;
     // ---- trial-sharded job: reduce the counters over the ranks inside the kernel ----
     PeerCall* peer;               // or null
     unsigned long long peer_epoch;

@@ -80,6 +80,8 @@ __device__ __forceinline__ void finish_single_call(const EquityParams& p, int la
     }
     if (lane == 0) { sc->work_counter = 0; sc->ticket = 0; }
     __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&sc->host->seq) = p.single_seq;   // the host spins on this word
 }
 
 // Trial-sharded job: the last warp of this rank's grid exchanges the counters with the other ranks over NVLink-mapped

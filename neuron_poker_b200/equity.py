@@ -23,7 +23,7 @@ from collections import Counter
 import numpy as np
 
 from . import _lib, ranges
-from .cards import HAND_TYPES, NO_CARD, card_ids, encode_query
+from .cards import HAND_TYPES, NO_CARD, _CARD_ID, card_ids, encode_query
 
 DEAL_UNIFORM = _lib.NPK_DEAL_UNIFORM
 DEAL_REFERENCE = _lib.NPK_DEAL_REFERENCE
@@ -62,45 +62,65 @@ def _u8(a):
 
 
 class _CallBuffers(threading.local):
-    """Per-thread argument and result buffers of the one-query calls: allocated once and addressed by integer (a ctypes
-    void* parameter accepts an int), so a get_equity call creates no arrays and no ctypes objects."""
+    """Per-thread result buffer of the one-query calls: allocated once and addressed by integer (a ctypes void* parameter
+    accepts an int), so a get_equity call creates no arrays and no ctypes objects."""
 
     def __init__(self):
-        self.inp = np.zeros(8, dtype=np.uint8)            # hole[2] board[5] players[1]
-        self.out = np.zeros(12, dtype=np.uint64)          # wins ties types[9] passes
-        a, o = self.inp.ctypes.data, self.out.ctypes.data
-        self.p_hole, self.p_board, self.p_npl = a, a + 2, a + 7
-        self.p_wins, self.p_ties, self.p_types, self.p_passes = o, o + 8, o + 16, o + 88
+        self.out = (ctypes.c_uint64 * 12)()               # wins ties types[9] passes
+        self.p_out = ctypes.addressof(self.out)
 
 
 _buffers = _CallBuffers()
+_PAD = tuple((((1 << (8 * m)) - 1) << (56 - 8 * m)) for m in range(6))      # 0xFF bytes for m MISSING board cards
+
+
+def _pack_query(player_cards, table_cards):
+    """hole[0] | hole[1] << 8 | board << 16 as one integer (0xFF for board cards not dealt yet).  Unknown card strings
+    raise ValueError like list.index in the reference (montecarlo_python.py:127-128); duplicates are caught by the library."""
+    ids = _CARD_ID
+    try:
+        hole = [ids[c] for c in player_cards]
+        board = [ids[c] for c in table_cards]
+    except (KeyError, TypeError):
+        hole, board = card_ids(player_cards), card_ids(table_cards)      # card ids, or the reference's ValueError
+    if len(hole) != 2:
+        raise ValueError("player_cards must hold exactly two cards, got %d" % len(hole))
+    nb = len(board)
+    if nb > 5:
+        raise ValueError("table_cards holds more than five cards")
+    packed = hole[0] | hole[1] << 8 | _PAD[5 - nb]
+    shift = 16
+    for c in board:
+        packed |= c << shift
+        shift += 8
+    return packed
 
 
 def equity_counts(player_cards, table_cards, players, runs, deal_mode="uniform", seed_value=None, win_types=False,
                   passes=False):
-    """One query through the host-buffer C entry point npk_equity_host: returns dict(wins, ties, runs[, win_types,
-    passes]).  `wins` = trials the hero strictly wins, `ties` = trials tied for best."""
+    """One query through the one-query C entry point npk_equity_one: returns dict(wins, ties, runs[, win_types, passes]).
+    `wins` = trials the hero strictly wins, `ties` = trials tied for best."""
     players = int(players)                      # numpy.int64 from sum(alive) is what the env passes (env.py:262)
     runs = int(runs)
     if players < 1:
         raise IndexError("list index out of range")     # reference: hands[winner] on an empty list
     if players > 10:
         raise ValueError("at most 10 players")
-    hole, board = encode_query(player_cards, table_cards)
+    packed = _pack_query(player_cards, table_cards)
     b = _buffers
-    b.inp[0:2] = hole
-    b.inp[2:7] = board
-    b.inp[7] = players
-    L = _lib.ensure_init(_device())
-    s = _next_seed() if seed_value is None else int(seed_value)
-    _lib.check(L.npk_equity_host(b.p_hole, b.p_board, b.p_npl, 1, runs, s & (2**64 - 1), _DEAL[deal_mode], b.p_wins, b.p_ties,
-                                 b.p_types if win_types else None, b.p_passes if passes else None))
+    L = _lib.ensure_current(_device())
+    s = _next_seed() if seed_value is None else int(seed_value) & (2**64 - 1)
+    rc = L.npk_equity_one(packed, players, runs, s, _DEAL[deal_mode], (1 if win_types else 0) | (2 if passes else 0), b.p_out)
+    if rc < 0:
+        if rc == -5:
+            raise ValueError("duplicate or invalid cards in player_cards / table_cards: " + L.npk_last_error().decode())
+        _lib.check(rc)
     out = b.out
-    res = {"wins": int(out[0]), "ties": int(out[1]), "runs": runs}
+    res = {"wins": out[0], "ties": out[1], "runs": runs}
     if win_types:
-        res["win_types"] = [int(x) for x in out[2:11]]
+        res["win_types"] = [out[i] for i in range(2, 11)]
     if passes:
-        res["passes"] = int(out[11])
+        res["passes"] = out[11]
     return res
 
 
@@ -130,7 +150,7 @@ def equity_counts_batch(hole, board, n_players, trials, seed_value=0, deal_mode=
 
 def get_equity(player_cards, table_cards, players, runs):
     """Get equity from a montecarlo run -- drop-in for tools/montecarlo_python.py:401-406 (reference dealing)."""
-    r = equity_counts(player_cards, table_cards, players, runs, deal_mode="reference")
+    r = equity_counts(player_cards, table_cards, players, runs, "reference")
     return (r["wins"] + r["ties"]) / runs
 
 
