@@ -547,6 +547,12 @@ def run_mc(args, wl, cx, deal, steps, warmup, peak=None, peak_detail=None, e2e=T
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     sampler = ClockSampler(cx.local_rank)
     sampler.start()
+    if by_trial:
+        # The ranks leave the host-side set-up above milliseconds apart, and a sharded step is a barrier between the GPUs:
+        # without this the early ranks' first timed step would be charged the late ranks' set-up.  One untimed step after a
+        # host barrier lines the GPUs' queues up on the device.
+        cx.barrier()
+        step(warmup)
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
     res = both
@@ -778,8 +784,8 @@ def main():
     extras["cfg2"] = brief(run_exact(args, workload("cfg2"), cx, steps=10))
     ref3, _ = run_mc(args, workload("cfg3"), cx, "reference", 20, 3, peak, peak_detail, e2e=False)
     extras["cfg3_reference_dealer"] = brief(ref3)
-    extras["cfg4"] = brief(run_strong(args, cx, "uniform", steps=10))
-    extras["cfg4_reference_dealer"] = brief(run_strong(args, cx, "reference", steps=4))
+    extras["cfg4"] = brief(run_strong(args, cx, "uniform", steps=20))
+    extras["cfg4_reference_dealer"] = brief(run_strong(args, cx, "reference", steps=10))
     extras["cfg5_uniform"] = brief(run_selfplay(args, workload("cfg5"), cx, "uniform", steps=30))
     extras["cfg5_reference_dealer"] = brief(run_selfplay(args, workload("cfg5"), cx, "reference", steps=30))
     extras["ranges"] = brief(run_ranges(args, workload("ranges"), cx, steps=5))

@@ -86,6 +86,12 @@ int64_t npk_equity_workspace_bytes(int64_t Q);
  *   seed, trial_offset, query_offset: trial t of query q uses the Philox4x32-10 stream with counter
  *                     (t + trial_offset, q + query_offset) and key = seed: results do not depend on how trials or
  *                     queries are partitioned over calls or GPUs.
+ *                     Uniformity of the dealing: indices are drawn by multiply-shift, two per 32-bit Philox word (the low
+ *                     product word of the first draw feeds the second).  The first index of a word deviates from uniform by
+ *                     less than 2^-26 relative, the second by less than 2^-20 (its input takes 2^32/n equally spaced values,
+ *                     n <= 50).  At 10^9 trials per query the induced error of an equity is below the 3-sigma sampling
+ *                     error by two orders of magnitude; callers who need more trials than that per query should split
+ *                     them over seeds.  No other approximation is made: the trial count is exact, nothing is truncated.
  *   wins_strict, ties [Q] u64, ACCUMULATED into (caller zeroes them): hero strictly best / tied for best.
  *                     reference equity = (wins_strict + ties) / trials  (ties count as wins, montecarlo_python.py:223-229)
  *   win_types  [Q,9] u64 or NULL: hand type of the hero whenever he wins or ties (winnerCardTypeList, :230-231, :244-248)

@@ -102,9 +102,23 @@ static __device__ __noinline__ void finish_peer(PeerCall* pc, unsigned long long
     const uint32_t world = pc->world, me = pc->rank;
     const uint32_t parity = (uint32_t)(epoch & 1ull);
     const size_t my_slot = ((size_t)parity * world + me) * pc->stride;
-    for (uint32_t i = lane; i < words; i += 32) {
-        const unsigned long long v = atomicExch(&pc->acc[i], 0ull);                 // read and reset for the next step
-        for (uint32_t r = 0; r < world; r++) pc->slots[r][my_slot + i] = v;         // peer stores (NVLink for r != me)
+    // push: four words per lane and batch, the reads (and resets) of the local counters first, then the peer stores --
+    // independent memory operations in flight instead of one dependent round trip after the other
+    for (uint32_t base = 0; base < words; base += 128) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = base + 32u * k + lane;
+            v[k] = i < words ? atomicExch(&pc->acc[i], 0ull) : 0ull;                // read and reset for the next step
+        }
+        for (uint32_t r = 0; r < world; r++) {
+            unsigned long long* dst = pc->slots[r] + my_slot;                       // NVLink for r != me
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = base + 32u * k + lane;
+                if (i < words) dst[i] = v[k];
+            }
+        }
     }
     __threadfence_system();
     __syncwarp();
@@ -121,11 +135,23 @@ static __device__ __noinline__ void finish_peer(PeerCall* pc, unsigned long long
         }
     }
     __syncwarp();
+    // sum the ranks' slots of this buffer (L2 is the point of coherence for the peers' writes: ld.cg after the acquire)
     const unsigned long long* mine = pc->slots[me] + (size_t)parity * world * pc->stride;
-    for (uint32_t i = lane; i < words; i += 32) {
-        unsigned long long s = 0;
-        for (uint32_t r = 0; r < world; r++) s += __ldcv(mine + (size_t)r * pc->stride + i);
-        totals[i] = s;
+    for (uint32_t base = 0; base < words; base += 128) {
+        unsigned long long sum[4] = {0, 0, 0, 0};
+#pragma unroll 4
+        for (uint32_t r = 0; r < world; r++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = base + 32u * k + lane;
+                if (i < words) sum[k] += __ldcg(mine + (size_t)r * pc->stride + i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = base + 32u * k + lane;
+            if (i < words) totals[i] = sum[k];
+        }
     }
     if (lane == 0) { pc->work_counter = 0; pc->ticket = 0; }
 }
