@@ -438,7 +438,9 @@ def run_selfplay(args, wl, cx, deal, steps=None):
 
 def run_ranges(args, wl, cx, steps=None):
     """Opponent ranges (montecarlo_python.py:136-181): 4,096 six-player flop queries x 1,000 trials, every
-    opponent restricted to the top 30 % of the reference's preflop ranking, reference dealer (equity_ranges_kernel<1>)."""
+    opponent restricted to the top 30 % of the reference's preflop ranking, reference dealer.  `value` = the pair-list
+    sampler (equity_ranges_fast_kernel, what a call without `passes` runs); the generic kernel that plays the reference's
+    attempt loop literally (and counts `passes`) is timed beside it."""
     import torch
     import neuron_poker_b200 as npk
     dev = cx.dev
@@ -449,30 +451,38 @@ def run_ranges(args, wl, cx, steps=None):
     out = {"wins": torch.zeros(Q, dtype=torch.int64, device=dev), "ties": torch.zeros(Q, dtype=torch.int64, device=dev),
            "passes": torch.zeros(Q, dtype=torch.int64, device=dev)}
 
-    def step(i):
-        for v in out.values():
-            if isinstance(v, torch.Tensor):
-                v.zero_()
-        npk.get_equity_ranges_batch(hole, board, npl, T, opponent_range=0.3, seed_value=300 + i, deal_mode=args.deal_ranges,
-                                    query_offset=cx.rank * Q, validate=False, passes=True, out=out)
+    def timed(with_passes):
+        def step(i):
+            for v in out.values():
+                if isinstance(v, torch.Tensor):
+                    v.zero_()
+            npk.get_equity_ranges_batch(hole, board, npl, T, opponent_range=0.3, seed_value=300 + i, deal_mode=args.deal_ranges,
+                                        query_offset=cx.rank * Q, validate=False, passes=with_passes, out=out)
+        for i in range(3):
+            step(i)
+        cx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return cx.max_over_ranks(e0.elapsed_time(e1)) / steps, float((out["wins"] + out["ties"]).double().mean().item() / T)
 
-    for i in range(3):
-        step(i)
-    cx.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        step(3 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = cx.max_over_ranks(e0.elapsed_time(e1)) / steps
+    ms_generic, eq_generic = timed(True)
     attempts = float(out["passes"].double().sum().item()) / (Q * T * (P - 1))
+    ms, eq = timed(False)
+    mode = 1 if args.deal_ranges == "reference" else 0
     return {"metric": METRIC, "value": Q * T * P * cx.world / (ms * 1e-3), "unit": UNIT, "n_gpus": cx.world, "steps": steps,
             "ms_per_step": ms, "scaling": "weak", "dtype": "u32", "data": "synthetic",
             "config": {"workload": wl["name"], "queries_per_gpu": Q, "trials": T, "players": P, "opponent_range": 0.3,
-                       "deal_mode": args.deal_ranges, "attempts_per_opponent_hand": attempts,
-                       "mean_equity": float((out["wins"] + out["ties"]).double().mean().item() / T)},
-            "gpu_launches": steps, "kernel": "equity_ranges_kernel<%d>" % (1 if args.deal_ranges == "reference" else 0)}
+                       "deal_mode": args.deal_ranges, "mean_equity": eq,
+                       "generic_kernel": {"kernel": "equity_ranges_kernel<%d>" % mode, "ms_per_step": ms_generic,
+                                          "value": Q * T * P * cx.world / (ms_generic * 1e-3), "mean_equity": eq_generic,
+                                          "attempts_per_opponent_hand": attempts,
+                                          "note": "plays the reference's attempt loop literally; the only variant that "
+                                                  "can count `passes`"}},
+            "gpu_launches": steps, "kernel": "equity_ranges_fast_kernel<%d>" % mode}
 
 
 def run_latency(args, wl, cx, with_cpu):

@@ -167,7 +167,11 @@ int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, 
  * deal_mode NPK_DEAL_REFERENCE reproduces the reference dealer including the quirk that the range test looks at
  * deck[i1], deck[i2] before popping (montecarlo_python.py:173-179); NPK_DEAL_UNIFORM is the unbiased counterpart
  * (two distinct uniform cards, redrawn until the class is allowed).  passes [Q] counts the draw attempts of hero and
- * opponents in both modes.  One generic kernel handles every mix of player counts and board sizes; the call is
+ * opponents in both modes -- a by-product of playing the reference's attempt loop literally, which only the generic kernel
+ * does: with passes == NULL the call uses a sampler that lists the allowed pairs of every query's deck once and redraws
+ * only on cards already dealt (same distribution of the dealt cards, several times faster; its Philox stream differs, so
+ * the counters of the two variants agree statistically, not bit for bit).  One kernel handles every mix of player counts
+ * and board sizes; the call is
  * asynchronous unless NPK_FLAG_VALIDATE is set, in which case the stream is synchronised and a range no remaining
  * hand can satisfy (one draw exceeded 65,536 attempts) is reported as NPK_ERR_RANGE.  Other arguments as above.
  */

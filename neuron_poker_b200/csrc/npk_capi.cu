@@ -588,6 +588,8 @@ int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint
     p.reference_dealer = deal_mode == NPK_DEAL_REFERENCE ? 1u : 0u;
     p.single = st.single;
     p.single_seq = ++st.single_seq;
+    const bool quick = !win_types && !passes && trials < (1ll << 32);
+    p.single_quick = quick ? 1u : 0u;
     p.work_counter = &st.single->work_counter;
     p.wins = &st.single->wins; p.ties = &st.single->ties;
     p.win_types = win_types ? st.single->win_types : nullptr;
@@ -596,18 +598,20 @@ int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint
     e = npk::launch_equity_uniform(players - 1, 5 - known, p, chunks, ds->sm_count, tuning().warps, st.stream);
     if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
     const volatile npk::SingleResult* r = st.single_host;
+    const volatile unsigned long long* flag = quick ? &r->quick.seq : &r->seq;
     bool arrived = false;
     for (long spins = 0; spins < 4000000; spins++) {              // a few hundred ms at most, then ask the driver
-        if (r->seq == p.single_seq) { arrived = true; break; }
+        if (*flag == p.single_seq) { arrived = true; break; }
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
 #endif
     }
     if (!arrived) {
         if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
-        if (r->seq != p.single_seq) return fail(NPK_ERR_CUDA, "the one-query kernel finished without publishing its result");
+        if (*flag != p.single_seq) return fail(NPK_ERR_CUDA, "the one-query kernel finished without publishing its result");
     }
     std::atomic_thread_fence(std::memory_order_acquire);
+    if (quick) { wins_strict[0] = r->quick.wins; ties[0] = r->quick.ties; return NPK_OK; }
     wins_strict[0] = r->wins; ties[0] = r->ties;
     if (win_types) for (int i = 0; i < 9; i++) win_types[i] = r->win_types[i];
     if (passes) passes[0] = r->passes;
@@ -955,7 +959,10 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
                              " (card id >= 52, duplicate cards, gap in the board, ghost card on the board or in the "
                              "hand, or players outside 1..10)");
     }
-    e = npk::launch_equity_ranges(deal_mode, p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
+    // `passes` is a by-product of the reference's attempt loop: only the generic kernel, which plays that loop literally,
+    // can count it; everyone else gets the pair-list sampler (csrc/npk_ranges.cu), which redraws far less often
+    e = passes ? npk::launch_equity_ranges(deal_mode, p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s)
+               : npk::launch_equity_ranges_fast(deal_mode, p, grid_for(*ds, Q * chunks, npk::kRefThreads / 32), s);
     if (e != cudaSuccess) return cuda_fail(e, "equity_ranges_kernel launch");
     if (validate) {
         uint32_t aborted = 0;

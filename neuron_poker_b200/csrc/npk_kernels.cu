@@ -602,15 +602,29 @@ static int uniform_warps(const DeviceTables& t, int nb, int forced)
     return w < 1 ? 1 : w;
 }
 
+constexpr int kMaxDevicesForAttr = 64;
+
 template <int NOPP, int NB>
 static cudaError_t launch_uniform_t(const EquityParams& p, long long items, int sm_count, int forced_warps, cudaStream_t s)
 {
+#ifdef NPK_UNIFORM_LEHMER
+    auto k = equity_refdeal_kernel<NOPP, NB>;      // experiment build: every deal mode through the Lehmer path
+#else
     auto k = p.reference_dealer ? equity_refdeal_kernel<NOPP, NB> : equity_uniform_kernel<NOPP, NB>;
+#endif
     const int warps = uniform_warps(p.tables, NB, forced_warps);
     const size_t smem = 128 + (size_t)p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes + kDescBytes +
                         (size_t)warps * (64 + (45 + NB) * 32) * 4;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    // the opt-in is per kernel and per device: ask the driver once, not on every launch of a 20 us call
+    static size_t opted[kMaxDevicesForAttr] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaSuccess;
+    if (dev < 0 || dev >= kMaxDevicesForAttr || opted[dev] != smem + 2 * (size_t)p.reference_dealer + 1) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < kMaxDevicesForAttr) opted[dev] = smem + 2 * (size_t)p.reference_dealer + 1;
+    }
     long long grid = (items + warps - 1) / warps;
     if (grid < 1) grid = 1;
     if (grid > sm_count) grid = sm_count;

@@ -20,6 +20,10 @@ constexpr int kRank7Threads = 1024;    // rank7 is latency-bound at one CTA per 
 struct SingleResult {             // in mapped host memory
     unsigned long long wins, ties, win_types[9], passes;
     unsigned long long seq;       // number of the call these values belong to: written last, the host spins on it
+    unsigned long long pad_[3];
+    // the common case (wins and ties only, fewer than 2^32 trials): ONE 16-byte store carries counters and sequence number,
+    // so the hand-over needs no system-wide fence between data and flag
+    struct __align__(16) Quick { unsigned int wins, ties; unsigned long long seq; } quick;
 };
 struct SingleCall {               // in device memory
     unsigned long long wins, ties, win_types[9], passes;
@@ -73,6 +77,7 @@ struct EquityParams {
     uint64_t inline_query;        // hole[2] | board[5] << 16 (bytes), used when `hole` is null
     SingleCall* single;           // device scratch + mapped host result block, or null
     unsigned long long single_seq;
+    uint32_t single_quick;        // 1: publish through SingleResult::quick
     // ---- trial-sharded job: reduce the counters over the ranks inside the kernel ----
     PeerCall* peer;               // or null
     unsigned long long peer_epoch;
@@ -104,6 +109,7 @@ cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long 
                                   cudaStream_t s);
 cudaError_t launch_equity_mixed(const EquityParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
+cudaError_t launch_equity_ranges_fast(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_rank7_colex(const DeviceTables& t, long long first, long long count, uint16_t* out, int grid, cudaStream_t s);
 cudaError_t launch_enum(const EnumParams& p, int grid, cudaStream_t s);

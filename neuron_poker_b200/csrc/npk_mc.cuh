@@ -73,12 +73,22 @@ __device__ __forceinline__ void finish_single_call(const EquityParams& p, int la
     last = __shfl_sync(0xffffffffu, last, 0);
     if (!last) return;
     __threadfence();
+    unsigned long long v = 0;
     if (lane < 12) {
         unsigned long long* src = &sc->wins;                           // wins, ties, win_types[9], passes are contiguous
-        const unsigned long long v = atomicExch(src + lane, 0ull);    // read and reset for the next call
-        (&sc->host->wins)[lane] = v;
+        v = atomicExch(src + lane, 0ull);                             // read and reset for the next call
     }
     if (lane == 0) { sc->work_counter = 0; sc->ticket = 0; }
+    if (p.single_quick) {
+        const unsigned long long t = __shfl_sync(0xffffffffu, v, 1);
+        if (lane == 0) {
+            const uint4 q = make_uint4((unsigned int)v, (unsigned int)t, (unsigned int)p.single_seq, (unsigned int)(p.single_seq >> 32));
+            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&sc->host->quick), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w)
+                         : "memory");                                                                     // one 16-byte store
+        }
+        return;
+    }
+    if (lane < 12) (&sc->host->wins)[lane] = v;
     __threadfence_system();
     __syncwarp();
     if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&sc->host->seq) = p.single_seq;   // the host spins on this word
@@ -496,7 +506,11 @@ __device__ __forceinline__ void refdeal_item(const EquityParams& p, const WarpCt
     constexpr int KNOWN = 5 - NB;
     constexpr int N = 50 - KNOWN;          // unseen cards
     constexpr int D = 2 * NOPP + NB;       // cards dealt per trial
+#ifdef NPK_UNIFORM_LEHMER       // experiment: UNIFORM index law (every pop uniform over the remaining list) through the same path
+    constexpr int NWR = (D + 1) / 2;
+#else
     constexpr int NWR = NOPP + (NB + 1) / 2;       // Philox words per trial
+#endif
     constexpr int NBLK2 = (2 * NWR + 3) / 4;       // Philox blocks per trial PAIR
     constexpr int G = (D + 3) / 4;
     static_assert(D <= N, "not enough cards");
@@ -537,6 +551,17 @@ __device__ __forceinline__ void refdeal_item(const EquityParams& p, const WarpCt
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             uint32_t raw[D > 0 ? D : 1];
+#ifdef NPK_UNIFORM_LEHMER
+            {
+                uint32_t remw = 0;
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const uint32_t x = (k & 1) ? remw : w[u * NWR + (k >> 1)];
+                    raw[k] = __umulhi(x, (uint32_t)(N - k));
+                    remw = x * (uint32_t)(N - k);
+                }
+            }
+#else
 #pragma unroll
             for (int o = 0; o < NOPP; o++) {
                 const uint32_t m = (uint32_t)(N - 2 * o - 1);              // n - 1
@@ -553,6 +578,7 @@ __device__ __forceinline__ void refdeal_item(const EquityParams& p, const WarpCt
                 raw[2 * NOPP + c] = __umulhi(x, m);
                 rem = x * m;
             }
+#endif
             uint32_t x4[G > 0 ? G : 1];
             lehmer_decode<D>(raw, x4);
 #pragma unroll

@@ -40,10 +40,13 @@ def seed(value=None):
     _seed_state["rng"] = None if value is None else np.random.RandomState(int(value) & 0xFFFFFFFF)
 
 
+_global_sample = np.random.random_sample       # bound method of numpy's global legacy RandomState (np.random.seed reseeds it)
+
+
 def _next_seed():
     """53 random bits from the global legacy RandomState (one call; the reference's own generator)."""
     rng = _seed_state["rng"]
-    return int((rng.random_sample() if rng is not None else np.random.random_sample()) * 9007199254740992.0)
+    return int((_global_sample() if rng is None else rng.random_sample()) * 9007199254740992.0)
 
 
 _device_cache = {}
@@ -165,6 +168,16 @@ def montecarlo(my_cards, cards_on_table, number_of_players, iterations):
     except ValueError as exc:                   # pybind11 surfaces std::runtime_error as RuntimeError
         raise RuntimeError("Card Type error!") from exc
     return (r["wins"] + r["ties"]) / iterations
+
+
+def numpy_montecarlo(my_cards, table_cards_alpha_numeric, iterations, player_amount):
+    """Call form of the numpy sibling, tools/montecarlo_numpy2.py:333-346: `my_cards` is [[card1, card2]], the argument order
+    is (cards, table, iterations, players) and the result is the equity in PER CENT.  Uniform dealing like the sibling's
+    argsort shuffle (:80-83), ties counted as wins -- i.e. what its (upstream skipped) tests expect
+    (tests/test_montecarlo_numpy.py: the Python tests' values, +-1 point); its upstream defects (the first two board cards
+    are dropped, :340; sole wins only, :309-313; results wrong post-flop) are NOT reproduced."""
+    r = equity_counts(my_cards[0], table_cards_alpha_numeric, player_amount, iterations, "uniform")
+    return 100.0 * (r["wins"] + r["ties"]) / int(iterations)
 
 
 def _u64(a):

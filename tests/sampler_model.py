@@ -213,16 +213,75 @@ def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_m
     return hero, opp, full, passes
 
 
+FAST_BLOCK0 = {"reference": 0xA0000000, "uniform": 0xE0000000}
+
+
+def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None):
+    """equity_ranges_fast_kernel (csrc/npk_ranges.cu): the same distribution of dealt cards as deal_ranges without the
+    attempt loop over the whole deck.  Per query the unordered pairs (a < b) of initially unseen cards whose class is
+    allowed are listed in ascending pair number b*(b-1)/2 + a; a draw takes entry hi32(w * len) and swaps it when bit 31 of
+    the low product word is set -> (sa, sb); it is redone when sa or sb has been dealt in this trial or (reference) sb is
+    the highest unseen card (the reference's i2 never reaches the last list element).  reference: hero keeps (sa, sb); an
+    opponent gets sa and, when sb > sa, the successor of sb among the unseen cards (pop(i1) shifted the list), else sb.
+    Board card: index hi32(w * (n-1)) (reference) / hi32(w * n) (uniform) of the ordered unseen cards.  One Philox word per
+    attempt / board card, blocks from 0xA0000000 (reference) / 0xE0000000 (uniform).  Returns (hero, opponents, board)."""
+    known = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set())
+    deck0 = [c for c in range(52) if c not in known]
+    avail = set(deck0)
+    ws = _Words(seed, query, trial)
+    ws.blk = FAST_BLOCK0[mode]
+
+    def pair_list(mask):
+        return [(a, b) for b in range(1, 52) for a in range(b) if a in avail and b in avail and _allowed(mask, a, b)]
+
+    opp_list = pair_list(opp_mask) if players > 1 else []
+    hero_list = pair_list(hero_mask) if hero_mask is not None else []
+
+    def draw(lst, is_hero):
+        if not lst:
+            raise RuntimeError("range cannot be satisfied")
+        for _ in range(MAX_ATTEMPTS):
+            prod = ws.next() * len(lst)
+            sa, sb = lst[prod >> 32]
+            if (prod & MASK) >> 31:
+                sa, sb = sb, sa
+            if sa not in avail or sb not in avail:
+                continue
+            if mode == "reference" and sb == max(avail):
+                continue
+            c1, c2 = sa, sb
+            if mode == "reference" and not is_hero and sb > sa:
+                c2 = min(c for c in avail if c > sb)
+            avail.discard(c1)
+            avail.discard(c2)
+            return [c1, c2]
+        raise RuntimeError("range cannot be satisfied")
+
+    hero = list(hole) if hero_mask is None else draw(hero_list, True)
+    opp = [draw(opp_list, False) for _ in range(players - 1)]
+    full = list(board)
+    while len(full) < 5:
+        n = len(avail)
+        j = (ws.next() * (n - 1 if mode == "reference" else n)) >> 32
+        c = sorted(avail)[j]
+        avail.discard(c)
+        full.append(c)
+    return hero, opp, full
+
+
 def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_offset=0, opp_mask=None, hero_mask=None,
-              ghost=None):
+              ghost=None, fast=False):
     """dict(wins, ties, passes, win_types[9]) of the modelled sampler scored by the oracle's rank ids.  With `opp_mask`
     the range dealers (deal_ranges) are modelled, otherwise the plain ones."""
     wins = ties = passes = 0
     types = [0] * 9
     for t in range(trial_offset, trial_offset + trials):
         if opp_mask is not None:
-            hole_t, opp, full, p = deal_ranges(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
-            passes += p
+            if fast:
+                hole_t, opp, full = deal_ranges_fast(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
+            else:
+                hole_t, opp, full, p = deal_ranges(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
+                passes += p
             hv = oracle.rank7(list(hole_t) + full)
             best = max([oracle.rank7(o + full) for o in opp], default=-1)
             if hv > best:

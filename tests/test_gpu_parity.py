@@ -368,6 +368,19 @@ def test_reference_montecarlo_test_spots(torch_mod, golden_enum):
         assert abs(np.mean(res) - s["test_expected_pct"]) < 3 and np.std(res) < 3, (s["name"], res)
 
 
+def test_numpy_sibling_call_form(torch_mod, golden_enum):
+    """numpy_montecarlo(my_cards, table, iterations, player_amount) -> per cent (tools/montecarlo_numpy2.py:333-346): the 19
+    spots of the sibling's own (upstream skipped) tests/test_montecarlo_numpy.py with their +-1 point rule, at 200,000 runs."""
+    npk.seed(2)
+    for s in golden_enum["spots"]:
+        got = npk.numpy_montecarlo([list(s["hero"])], list(s["board"]), 200000, s["players"])
+        assert abs(got - s["test_expected_pct"]) < 1.0, (s["name"], got, s["test_expected_pct"])
+        if s.get("uniform"):                                   # exact (win, tie, lose) counts under uniform dealing
+            w, t, l = s["uniform"]
+            exact = (w + t) / (w + t + l)
+            assert abs(got / 100 - exact) < 4 * sigma(exact, 200000) + 1e-9, (s["name"], got, exact)
+
+
 def test_invalid_queries_are_reported(torch_mod):
     torch = torch_mod
     with pytest.raises(_lib.NpkError) as e:

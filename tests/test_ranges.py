@@ -51,6 +51,34 @@ def test_oracle_reproduces_reference_range_runs(golden_ranges):
         assert got["next_randint"] == run["next_randint_0_1000000"], run["name"]
 
 
+def test_pair_list_specification_deals_the_reference_distribution_exactly():
+    """The pair-list sampler (sampler_model.deal_ranges_fast) against the reference's literal loop, by exact enumeration on one
+    opponent draw: for every state (set of unseen cards) tried, the accepted (entry, orientation) outcomes map one-to-one onto
+    the (i1, i2) the reference accepts, and deal the same two cards."""
+    import itertools
+    import random
+    rnd = random.Random(5)
+    mask = ranges.opponent_mask(0.3)
+    for _ in range(6):
+        deck = sorted(rnd.sample(range(52), rnd.randint(12, 20)))
+        n = len(deck)
+        # the reference: i1 in [0,n), i2 in [0,n-1), i1 != i2, class(deck[i1], deck[i2]) allowed; pop(i1), pop(i2)
+        ref = []
+        for i1, i2 in itertools.product(range(n), range(n - 1)):
+            if i1 != i2 and sampler_model._allowed(mask, deck[i1], deck[i2]):
+                d = list(deck)
+                ref.append((d.pop(i1), d.pop(i2)))
+        # the pair list: unordered allowed pairs, both orientations, sb != max, successor rule
+        fast = []
+        pairs = [(a, b) for b in deck for a in deck if a < b and sampler_model._allowed(mask, a, b)]
+        for a, b in pairs:
+            for sa, sb in ((a, b), (b, a)):
+                if sb == max(deck):
+                    continue
+                fast.append((sa, min(c for c in deck if c > sb) if sb > sa else sb))
+        assert sorted(ref) == sorted(fast) and len(ref) > 0
+
+
 def test_sampler_specification_with_ranges_converges_to_the_oracle():
     """The Philox-driven specification of libnpk's range dealers (tests/sampler_model.py) and the oracle's MT19937-driven
     restatement sample the same distributions: equities agree within 3 sigma of their combined standard error."""
@@ -76,6 +104,10 @@ def test_sampler_specification_with_ranges_converges_to_the_oracle():
             p_or = (w + t) / 40000
         se = (p_or * (1 - p_or) * (1 / T + 1 / 40000)) ** 0.5
         assert abs(p_model - p_or) < 3 * se + 1e-9, (mode, hero, hero_cls, p_model, p_or, se)
+        f = sampler_model.run_model(oracle, mode, 199, 0, h, b, players, T, opp_mask=ranges.mask_from_classes(opp),
+                                    hero_mask=ranges.mask_from_classes(hero_cls) if hero_cls else None, ghost=g, fast=True)
+        p_fast = (f["wins"] + f["ties"]) / T
+        assert abs(p_fast - p_or) < 3 * se + 1e-9, ("pair list", mode, hero, hero_cls, p_fast, p_or, se)
 
 
 # ---- GPU: libnpk's range kernels ---------------------------------------------------------------------------------------
@@ -116,6 +148,57 @@ def test_range_kernels_match_the_sampler_specification(cuda_device):
                                     ghost=_ids(ghost) if ghost else None)
         got = (int(out["wins"][0]), int(out["ties"][0]), int(out["passes"][0]), [int(x) for x in out["win_types"][0]])
         assert got == (m["wins"], m["ties"], m["passes"], m["win_types"]), (mode, hero, hero_cls, got, m)
+
+
+@pytest.mark.gpu
+def test_pair_list_range_kernel_matches_its_specification(cuda_device):
+    """Without `passes` the range entry point runs equity_ranges_fast_kernel (pair-list sampler, csrc/npk_ranges.cu): wins, ties
+    and win types equal its Python specification (sampler_model.deal_ranges_fast) bit for bit in both dealing modes, with hero
+    ranges and ghost cards, at a trial offset."""
+    import neuron_poker_b200 as npk
+    T, off = 96, 1000
+    for i, (mode, hero, hero_cls, board, players, opp, ghost) in enumerate(RANGE_CASES):
+        b = _ids(board)
+        out = npk.get_equity_ranges_batch(
+            None if hero is None else np.array([_ids(hero)], dtype=np.uint8),
+            np.array([b + [255] * (5 - len(b))], dtype=np.uint8), np.array([players], dtype=np.uint8), T,
+            opponent_range=opp, hero_range=hero_cls, ghost=None if ghost is None else np.array([_ids(ghost)], dtype=np.uint8),
+            seed_value=177 + i, deal_mode=mode, trial_offset=off, query_offset=5, win_types=True, passes=False)
+        m = sampler_model.run_model(oracle, mode, 177 + i, 5, _ids(hero) if hero else None, b, players, T, trial_offset=off,
+                                    opp_mask=ranges.opponent_mask(opp),
+                                    hero_mask=ranges.mask_from_classes(hero_cls) if hero_cls else None,
+                                    ghost=_ids(ghost) if ghost else None, fast=True)
+        got = (int(out["wins"][0]), int(out["ties"][0]), [int(x) for x in out["win_types"][0]])
+        assert got == (m["wins"], m["ties"], m["win_types"]), (mode, hero, hero_cls, got, m)
+
+
+@pytest.mark.gpu
+def test_pair_list_range_kernel_within_3_sigma_of_the_oracle_and_of_the_generic_kernel(cuda_device):
+    """The pair-list sampler deals the reference's distribution: 4 M trials against 400 k oracle trials (the MT19937-driven
+    restatement of the reference's loop) and against the generic kernel that plays that loop literally."""
+    import neuron_poker_b200 as npk
+    T, TO = 4_000_000, 400_000
+    for i, (mode, hero, hero_cls, board, players, opp, ghost) in enumerate(RANGE_CASES[:8]):
+        b = _ids(board)
+        args = (None if hero is None else np.array([_ids(hero)], dtype=np.uint8),
+                np.array([b + [255] * (5 - len(b))], dtype=np.uint8), np.array([players], dtype=np.uint8), T)
+        kw = dict(opponent_range=opp, hero_range=hero_cls, ghost=None if ghost is None else np.array([_ids(ghost)], dtype=np.uint8),
+                  deal_mode=mode)
+        fast = npk.get_equity_ranges_batch(*args, seed_value=4321 + i, passes=False, **kw)
+        slow = npk.get_equity_ranges_batch(*args, seed_value=8765 + i, passes=True, **kw)
+        p_fast = (int(fast["wins"][0]) + int(fast["ties"][0])) / T
+        p_slow = (int(slow["wins"][0]) + int(slow["ties"][0])) / T
+        opp_cls = opp if isinstance(opp, set) else ranges.allowed_classes(opp)
+        if mode == "reference":
+            o = oracle.mc_reference_ranges(hero, board, players, TO, 21 + i, opp_cls, hero_classes=hero_cls, ghost=ghost)
+            p_or = o["wins"] / TO
+        else:
+            w, t, a = oracle.mc_uniform_ranges(hero, board, players, TO, 21 + i, opp_cls, hero_classes=hero_cls, ghost=ghost)
+            p_or = (w + t) / TO
+        se = (p_or * (1 - p_or) * (1 / T + 1 / TO)) ** 0.5
+        assert abs(p_fast - p_or) < 3 * se + 1e-9, (mode, hero, hero_cls, p_fast, p_or, se)
+        se2 = (max(p_slow * (1 - p_slow), 1e-9) * 2 / T) ** 0.5
+        assert abs(p_fast - p_slow) < 3.5 * se2 + 1e-9, (mode, hero, hero_cls, p_fast, p_slow, se2)
 
 
 @pytest.mark.gpu

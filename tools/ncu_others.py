@@ -32,7 +32,7 @@ if what in ("ranges", "all"):
     npl = torch.full((Q,), 6, dtype=torch.uint8)
     for _ in range(3):
         npk.get_equity_ranges_batch(cards[:, :2].contiguous(), board, npl, 1000, opponent_range=0.3, deal_mode="reference",
-                                    validate=False)
+                                    validate=False, passes=len(sys.argv) > 2 and sys.argv[2] == "generic")
 if what in ("holdem", "all"):
     tb = HoldemTables(65536, n_players=6, seed=7, autoplay=[1] * 6, device=dev)
     agents = EquityAgents.equity_vs_random()
