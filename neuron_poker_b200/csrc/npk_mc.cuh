@@ -395,7 +395,8 @@ struct WordStream {
     __device__ __forceinline__ uint32_t next()
     {
         if (have == 0) { philox4x32_10(c0, c1, c2, blk++, k0, k1, w); have = 4; }
-        uint32_t r = w[4 - have];
+        const uint32_t r = w[0];                 // words leave in order; the rest moves up (no dynamic indexing: the
+        w[0] = w[1]; w[1] = w[2]; w[2] = w[3];   // block stays in registers instead of local memory)
         have--;
         return r;
     }

@@ -136,54 +136,60 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_fast_kernel(cons
             int n = n0;
             uint32_t best = 0;
             uint32_t oc1[9], oc2[9];
-            if (active) {
-                // hand -1 = the hero when drawn from a range, hands 0.. = the opponents
-                for (int o = p.hero_range ? -1 : 0; o < nopp && active; o++) {
-                    const bool is_hero = o < 0;
-                    const uint16_t* list = is_hero ? hero_list : opp_list;
-                    const uint32_t len = is_hero ? n_hero_list : n_opp_list;
-                    uint32_t c1 = 0, c2 = 0, tries = 0;
-                    for (;;) {
-                        if (++tries > kMaxRangeAttempts) { atomicExch(p.abort_flag, 1u); active = false; break; }
-                        const uint64_t prod = (uint64_t)rs.next() * len;
-                        const uint32_t pr = list[(uint32_t)(prod >> 32)];
-                        uint32_t sa = pr & 255u, sb = pr >> 8;
-                        if ((uint32_t)prod >> 31) { const uint32_t t = sa; sa = sb; sb = t; }
-                        if (!((avail >> sa) & (avail >> sb) & 1ull)) continue;         // one of them was dealt earlier in this trial
-                        if (MODE == 1 && sb == 63u - (uint32_t)__clzll((long long)avail)) continue;   // i2 never reaches the last element
-                        c1 = sa;
-                        c2 = sb;
-                        if (MODE == 1 && !is_hero && sb > sa)                          // pop(i1) shifted the list: successor of sb
-                            c2 = sb + (uint32_t)__ffsll((long long)(avail >> (sb + 1u)));
-                        break;
-                    }
+            // one hand from a pair list (see the header): returns false when the attempt limit is hit
+            auto draw = [&](const uint16_t* list, uint32_t len, bool is_hero, uint32_t& c1, uint32_t& c2) {
+                for (uint32_t tries = 0; tries < kMaxRangeAttempts; tries++) {
+                    const uint64_t prod = (uint64_t)rs.next() * len;
+                    const uint32_t pr = list[(uint32_t)(prod >> 32)];
+                    uint32_t sa = pr & 255u, sb = pr >> 8;
+                    if ((uint32_t)prod >> 31) { const uint32_t t = sa; sa = sb; sb = t; }
+                    if (!((avail >> sa) & (avail >> sb) & 1ull)) continue;             // one of them was dealt earlier in this trial
+                    if (MODE == 1 && sb == 63u - (uint32_t)__clzll((long long)avail)) continue;   // i2 never reaches the last element
+                    c1 = sa;
+                    c2 = sb;
+                    if (MODE == 1 && !is_hero && sb > sa)                              // pop(i1) shifted the list: successor of sb
+                        c2 = sb + (uint32_t)__ffsll((long long)(avail >> (sb + 1u)));
                     avail &= ~((1ull << c1) | (1ull << c2));
                     n -= 2;
-                    if (is_hero) { h0 = c1; h1 = c2; }
-                    else { oc1[o] = stab.desc[c1]; oc2[o] = stab.desc[c2]; }
+                    return true;
+                }
+                atomicExch(p.abort_flag, 1u);
+                return false;
+            };
+            if (active && p.hero_range) active = draw(hero_list, n_hero_list, true, h0, h1);
+            // the opponents, unrolled over the nine seats so that their cards stay in registers
+#pragma unroll
+            for (int o = 0; o < 9; o++) {
+                if (o < nopp && active) {
+                    uint32_t c1 = 0, c2 = 0;
+                    active = draw(opp_list, n_opp_list, false, c1, c2);
+                    oc1[o] = stab.desc[c1]; oc2[o] = stab.desc[c2];
                 }
             }
             const uint32_t hd0 = stab.desc[h0], hd1 = stab.desc[h1];
             uint32_t bsum = board_sum, bcnt = board_cnt;
-            uint32_t bd[5];
-            int nbd = 0;
-            if (active) {
-                for (int k = known; k < 5; k++) {
+            uint32_t bd[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                if (k >= known && active) {
                     const uint32_t j = __umulhi(rs.next(), (uint32_t)(MODE == 1 ? n - 1 : n));
                     const int c = select_bit(avail, (int)j);
                     avail &= ~(1ull << c);
                     n--;
                     const uint32_t d = stab.desc[c];
-                    bd[nbd++] = d;
+                    bd[k] = d;
                     bsum += d; bcnt += suit_inc(d);
                 }
             }
             const BoardFlush bf = board_flush(bcnt);
             uint32_t bfield = prmt(board_lo, board_hi, bf.sel);
-            for (int k = 0; k < nbd; k++) bfield |= flush_bit(bd[k], bf.fsx);
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                if (k >= known && active) bfield |= flush_bit(bd[k], bf.fsx);
             const uint32_t hv = eval_player(st, bsum + hd0 + hd1, bfield | flush_bit(hd0, bf.fsx) | flush_bit(hd1, bf.fsx), bf.thr);
-            if (active)
-                for (int o = 0; o < nopp; o++)
+#pragma unroll
+            for (int o = 0; o < 9; o++)
+                if (o < nopp && active)
                     best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
                                                  bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
             const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
