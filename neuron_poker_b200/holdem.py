@@ -376,12 +376,29 @@ class HoldemTable(object):
         self._get_environment()
 
     def step(self, action):
-        """env.py:170-200: autoplay agents act until a seat driven from outside is to move (or the game is over)."""
+        """env.py:170-200: autoplay agents act until a seat driven from outside is to move (or the game is over).
+        The reward of an autoplay sequence follows the reference to the letter (:178-188): `acting_agent` is the seat that was
+        to move when step() was entered, and after EVERY legal autoplay action `_calculate_reward` (:282-306) runs for that seat
+        -- the final reward when the game is over, else the difference of its last two funds-history rows once there are two,
+        else whatever the reward was before (the device step only rewards externally driven seats, :194-197)."""
         self.reward = 0
         if self._autoplay():
+            acting = self.current_player.seat
             while self._autoplay() and not self.done and self.legal_moves:
                 a = self.current_player.agent_obj.action(self.legal_moves, self.observation, self.info, self.funds_history)
+                before = self.reward
+                legal = Action(int(getattr(a, "value", a))) in self.legal_moves
                 self._apply(a)
+                if not legal:
+                    continue                                   # _illegal_move sets its own reward (kept from the device step)
+                s = self._s
+                if self.done:
+                    won = -1 if hasattr(self.players[self.winner_ix].agent_obj, "autoplay") else 1
+                    self.reward = self.initial_stacks * len(self.players) * won
+                elif int(s["funds_rows"]) > 1:
+                    self.reward = float(s["funds_last"][acting]) - float(s["funds_prev"][acting])
+                else:
+                    self.reward = before
         else:
             self._apply(action)
         return self.array_everything, self.reward, self.done, False, self.info

@@ -190,6 +190,61 @@ def build_traces():
     print("env_traces.npz written:", sum(m["steps"] for m in meta), "steps in", len(meta), "games")
 
 
+class AutoSeat:
+    """Deterministic autoplay agent for the autoplay traces: the k-th call picks legal move (5k + 3) mod #moves among the
+    legal moves sorted by value, all-ins excluded unless nothing else is legal (tests/test_holdem.py holds the same class)."""
+    autoplay = True
+
+    def __init__(self):
+        self.name, self.k = "auto", 0
+
+    def action(self, legal_moves, observation, info, funds_history):
+        moves = sorted((m for m in legal_moves if m != Action.ALL_IN), key=lambda m: m.value) or list(legal_moves)
+        self.k += 1
+        return moves[(5 * self.k + 3) % len(moves)]
+
+
+def build_autoplay_traces():
+    """Games that mix autoplay agents with externally driven seats (gym_env/env.py:170-200): what step() returns -- reward,
+    done -- and who is to move, after every call.  Table t of seed SEED + 1000 + game deals from the Philox stream of table 0."""
+    games = []
+    for game, (pattern, stacks) in enumerate([("EAA", 30), ("AEA", 100), ("AAEA", 20), ("EAEAAA", 50), ("AE", 40), ("EA", 12),
+                                              ("AAAE", 100), ("AEAEA", 8)]):
+        seed = SEED + 1000 + game
+        dealer = Dealer(seed, 0)
+        rng = random.Random(2000 + game)
+        real_randint = np.random.randint
+        np.random.randint = dealer.randint
+        calls = []
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                env = HoldemTable(initial_stacks=stacks, small_blind=1, big_blind=2, funds_plot=False)
+                for ch in pattern:
+                    env.add_player(AutoSeat() if ch == "A" else Seat())
+                env.reset()
+                while not env.done and len(calls) < 300 and env.legal_moves:
+                    if hasattr(env.current_player.agent_obj, "autoplay"):
+                        a = None
+                        _, reward, done, _, _ = env.step(Action.FOLD)      # ignored: an autoplay seat is to move
+                    else:
+                        w = [0.05 if x == Action.ALL_IN else 1.0 for x in env.legal_moves]
+                        a = rng.choices(env.legal_moves, weights=w)[0]
+                        _, reward, done, _, _ = env.step(a)
+                    cp = env.current_player
+                    calls.append({"action": None if a is None else a.value, "reward": float(reward), "done": bool(done),
+                                  "current_player": cp.seat if hasattr(cp, "seat") else -1,
+                                  "stacks": [float(p.stack) for p in env.players], "stage": env.stage.value,
+                                  "rng_counter": dealer.k})
+        finally:
+            np.random.randint = real_randint
+        games.append({"seed": seed, "pattern": pattern, "initial_stacks": stacks, "calls": calls})
+        print(" autoplay game", game, pattern, "calls", len(calls), "done", calls[-1]["done"] if calls else None,
+              "nonzero rewards", sum(1 for c in calls if c["reward"]))
+    with open(os.path.join(HERE, "autoplay_traces.json"), "w") as f:
+        json.dump({"source": "gym_env/env.py::HoldemTable.step with autoplay agents (unmodified reference)", "games": games}, f)
+    print("autoplay_traces.json written")
+
+
 def build_agent_cases():
     from agents.agent_consider_equity import Player
     rng = random.Random(5)
@@ -207,5 +262,7 @@ def build_agent_cases():
 
 
 if __name__ == "__main__":
-    build_traces()
-    build_agent_cases()
+    if "--autoplay-only" not in sys.argv:
+        build_traces()
+        build_agent_cases()
+    build_autoplay_traces()

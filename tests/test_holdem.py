@@ -359,3 +359,48 @@ def test_single_table_front_end_runs_the_reference_agent_protocol(cuda_device):
     assert 0.0 <= info["player_data"]["equity_to_river_alive"] <= 1.0
     env.step(Action.CHECK)                                # illegal here: costs -1, nothing else happens
     assert env.reward == -1 and env.current_player.seat == 4
+
+
+@pytest.mark.gpu
+def test_autoplay_rewards_follow_the_reference(cuda_device):
+    """tests/golden/autoplay_traces.json: eight games of the UNMODIFIED reference env mixing autoplay agents and externally
+    driven seats (make_env_golden.py::build_autoplay_traces).  holdem.HoldemTable returns the same reward and done flag from every
+    step() call, hands the move to the same seat and ends with the same stacks -- in particular the reward an autoplay sequence
+    reports for the seat that was to move when step() was entered (gym_env/env.py:178-188, :282-306)."""
+    import json
+    from neuron_poker_b200.holdem import Action, HoldemTable
+
+    class AutoSeat:                                        # the same deterministic agent as in make_env_golden.py
+        autoplay = True
+
+        def __init__(self):
+            self.name, self.k = "auto", 0
+
+        def action(self, legal_moves, observation, info, funds_history):
+            moves = sorted((m for m in legal_moves if m != Action.ALL_IN), key=lambda m: m.value) or list(legal_moves)
+            self.k += 1
+            return moves[(5 * self.k + 3) % len(moves)]
+
+    class Human:
+        name = "h"
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "autoplay_traces.json")) as f:
+        games = json.load(f)["games"]
+    checked = 0
+    for g in games:
+        env = HoldemTable(initial_stacks=g["initial_stacks"], small_blind=1, big_blind=2, seed=g["seed"])
+        env.get_equity = lambda *a: 0.5                    # the traces were recorded with this constant
+        for ch in g["pattern"]:
+            env.add_player(AutoSeat() if ch == "A" else Human())
+        env.reset()
+        for i, c in enumerate(g["calls"]):
+            a = Action.FOLD if c["action"] is None else Action(c["action"])
+            _, reward, done, _, _ = env.step(a)
+            cp = env.current_player.seat if env.current_player is not None else -1
+            where = (g["pattern"], i, c)
+            assert reward == c["reward"] and done == c["done"], (where, reward, done)
+            assert [p.stack for p in env.players] == c["stacks"], (where, [p.stack for p in env.players])
+            if not done:
+                assert cp == c["current_player"] and env.stage.value == c["stage"], (where, cp, env.stage)
+            checked += 1
+    assert checked > 250
