@@ -796,8 +796,8 @@ def main():
     extras["cfg3_reference_dealer"] = brief(ref3)
     extras["cfg4"] = brief(run_strong(args, cx, "uniform", steps=20))
     extras["cfg4_reference_dealer"] = brief(run_strong(args, cx, "reference", steps=10))
-    extras["cfg5_uniform"] = brief(run_selfplay(args, workload("cfg5"), cx, "uniform", steps=30))
-    extras["cfg5_reference_dealer"] = brief(run_selfplay(args, workload("cfg5"), cx, "reference", steps=30))
+    extras["cfg5_uniform"] = brief(run_selfplay(args, workload("cfg5"), cx, "uniform", steps=60))
+    extras["cfg5_reference_dealer"] = brief(run_selfplay(args, workload("cfg5"), cx, "reference", steps=60))
     extras["ranges"] = brief(run_ranges(args, workload("ranges"), cx, steps=5))
     line["workloads"] = extras
     if with_cpu:
