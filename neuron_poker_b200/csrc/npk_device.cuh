@@ -45,7 +45,7 @@ struct SmemTables {
 // against its bounds, and the shuffled deck is compared with the canonical one after every work item (a racing or missing
 // restore shows up there).  A failed check records its code in DeviceTables::check (npk_checked_status reads it).
 // Codes: 1 rowoff gather, 2 value gather, 3 flush gather, 4 Fisher-Yates slot, 5 Lehmer slot, 6 duplicate Lehmer slot,
-//        7 deck not restored, 8 descriptor index, 9 enumeration pair list.
+//        7 deck not restored, 8 descriptor index, 9 pair list of the range sampler (entry index, card ids).
 #ifdef NPK_CHECKED
 #define NPK_CHECK(ptr, cond, code) do { if (!(cond)) atomicMax((ptr), (unsigned)(code)); } while (0)
 #else

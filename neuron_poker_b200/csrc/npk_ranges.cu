@@ -140,8 +140,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_fast_kernel(cons
             auto draw = [&](const uint16_t* list, uint32_t len, bool is_hero, uint32_t& c1, uint32_t& c2) {
                 for (uint32_t tries = 0; tries < kMaxRangeAttempts; tries++) {
                     const uint64_t prod = (uint64_t)rs.next() * len;
+                    NPK_CHECK(st.check, (uint32_t)(prod >> 32) < len && len <= 1344u, 9);
                     const uint32_t pr = list[(uint32_t)(prod >> 32)];
                     uint32_t sa = pr & 255u, sb = pr >> 8;
+                    NPK_CHECK(st.check, sa < 52u && sb < 52u && sa != sb, 9);
                     if ((uint32_t)prod >> 31) { const uint32_t t = sa; sa = sb; sb = t; }
                     if (!((avail >> sa) & (avail >> sb) & 1ull)) continue;             // one of them was dealt earlier in this trial
                     if (MODE == 1 && sb == 63u - (uint32_t)__clzll((long long)avail)) continue;   // i2 never reaches the last element
