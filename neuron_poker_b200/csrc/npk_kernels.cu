@@ -13,6 +13,7 @@
 // Everything is integer work on 32-bit lanes: no tensor cores, no floating point.  One trial per lane; the rank
 // tables (about 129 KB) are staged once per CTA into shared memory by the bulk-copy engine and gathered with 16-bit
 // LDS; win / tie counts are reduced with warp REDUX and one 64-bit RED per (warp, work item).
+#include <atomic>
 #include <cstdlib>
 #include "npk_mc.cuh"
 
@@ -616,7 +617,7 @@ static cudaError_t launch_uniform_t(const EquityParams& p, long long items, int 
     const size_t smem = 128 + (size_t)p.tables.value_bytes + p.tables.rowoff_bytes + p.tables.flush_bytes + kDescBytes +
                         (size_t)warps * (64 + (45 + NB) * 32) * 4;
     // the opt-in is per kernel and per device: ask the driver once, not on every launch of a 20 us call
-    static size_t opted[kMaxDevicesForAttr] = {};
+    static std::atomic<size_t> opted[kMaxDevicesForAttr];          // zero-initialised; several host threads may launch
     int dev = 0;
     cudaGetDevice(&dev);
     cudaError_t e = cudaSuccess;

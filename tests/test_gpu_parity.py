@@ -509,3 +509,47 @@ def test_sync_free_mixed_batches_equal_the_classified_path(torch_mod):
                                  trial_offset=3, query_offset=9)
         sel = torch_mod.as_tensor((npl == 2) | (npl == 3)).to(c["wins"].device)
         assert (c["wins"][sel] == a["wins"][sel]).all() and (c["wins"][~sel] == 0).all() and (c["ties"][~sel] == 0).all()
+
+
+def test_host_entry_points_are_reentrant(torch_mod):
+    """npk_equity_one / npk_equity_host from several host threads at once (ctypes releases the GIL): every thread owns its
+    stream, staging and one-query scratch inside libnpk, so concurrent calls return exactly what the same calls return alone."""
+    import threading
+    spots = [({"AS", "KS"}, {"2C", "7D", "KH"}, 6), ({"3H", "3S"}, {"8S", "4S", "QH", "8C", "4H"}, 2), ({"TD", "7D"}, set(), 4),
+             ({"QC", "QD"}, {"2C", "7D", "KH", "9S"}, 3)]
+    want = {}
+    for i, (h, b, n) in enumerate(spots):
+        for mode in ("uniform", "reference"):
+            r = npk.equity_counts(h, b, n, 5000, deal_mode=mode, seed_value=100 + i, win_types=(i & 1) == 1)
+            want[(i, mode)] = (r["wins"], r["ties"], tuple(r.get("win_types", ())))
+    rng = np.random.default_rng(4)
+    cards = np.stack([rng.permutation(52)[:5] for _ in range(33)]).astype(np.uint8)
+    bh, bb = cards[:, :2].copy(), np.full((33, 5), NO, dtype=np.uint8)
+    bb[:, :3] = cards[:, 2:]
+    bn = np.full(33, 5, dtype=np.uint8)
+    batch_want = npk.equity_counts_batch(bh, bb, bn, 640, seed_value=9)
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(60):
+                i = (tid + rep) % len(spots)
+                mode = "reference" if (tid + rep) & 1 else "uniform"
+                h, b, n = spots[i]
+                r = npk.equity_counts(h, b, n, 5000, deal_mode=mode, seed_value=100 + i, win_types=(i & 1) == 1)
+                got = (r["wins"], r["ties"], tuple(r.get("win_types", ())))
+                if got != want[(i, mode)]:
+                    errors.append((tid, rep, got, want[(i, mode)]))
+                if rep % 15 == 0:
+                    o = npk.equity_counts_batch(bh, bb, bn, 640, seed_value=9)
+                    if not ((o["wins"] == batch_want["wins"]).all() and (o["ties"] == batch_want["ties"]).all()):
+                        errors.append((tid, rep, "batch"))
+        except Exception as exc:          # noqa: BLE001
+            errors.append((tid, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
