@@ -5,12 +5,14 @@
 //                                       with the C++ sibling's dealing semantics (Montecarlo.cpp:293-312)
 //   equity_refdeal_kernel<NOPP,NB>  K1' same loop with the Python reference's own (biased) dealer
 //                                       (montecarlo_python.py:165-189)
-//   equity_ranges_kernel<MODE>      K1'' generic dealer with opponent / hero ranges and ghost cards
+//   equity_ranges_kernel<MODE>      K1'' generic dealer with opponent / hero ranges and ghost cards (the reference's attempt
+//                                       loop played literally; the pair-list sampler lives in npk_ranges.cu, the persistent
+//                                       all-shapes kernel for mixed batches in npk_mixed.cu, the per-trial code in npk_mc.cuh)
 //   rank7_kernel / rank7_colex      K2  batched 7-card rank ids (hand_evaluator.py:27-119 `_calc_score` ordering)
 //   enum_headsup_kernel             K3  exact heads-up enumeration of opponents and missing board cards
 //   showdown_kernel                 K4  batched get_winner (hand_evaluator.py:9-17)
 //
-// Everything is integer work on 32-bit lanes: no tensor cores, no floating point.  One trial per lane; the rank
+// Everything is integer work on 32-bit lanes: no tensor cores, no floating point.  Two trials per lane and iteration; the rank
 // tables (about 129 KB) are staged once per CTA into shared memory by the bulk-copy engine and gathered with 16-bit
 // LDS; win / tie counts are reduced with warp REDUX and one 64-bit RED per (warp, work item).
 #include <atomic>
@@ -373,6 +375,16 @@ __global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p
     __shared__ unsigned long long s_acc[3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
+    // The list of slot pairs (a < b), pair number C(b,2) + a, does not depend on the query: a deck of n cards uses its first
+    // n(n-1)/2 entries.  Built once per CTA (round 1 rebuilt it for every query: one thread walked up to 46 entries alone,
+    // which cost a river query -- 990 matchups, two per thread -- about as much as the matchups themselves).
+    for (int i = threadIdx.x; i < 1326; i += blockDim.x) {
+        int b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)i)) * 0.5f);
+        while (b * (b - 1) / 2 > i) b--;
+        while ((b + 1) * b / 2 <= i) b++;
+        s_pair[i] = (uint16_t)((i - b * (b - 1) / 2) | b << 8);
+    }
+
     for (long long q = blockIdx.x; q < p.nq; q += gridDim.x) {
         int known = 0;
         for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
@@ -391,8 +403,6 @@ __global__ void __launch_bounds__(kAuxThreads, 1) enum_kernel(const EnumParams p
         if (threadIdx.x < 3) s_acc[threadIdx.x] = 0;
         for (int c = threadIdx.x; c < 52; c += blockDim.x)
             if (avail >> c & 1ull) s_deck[__popcll(avail & ((1ull << c) - 1ull))] = p.tables.desc[c];
-        for (int b = threadIdx.x; b < n; b += blockDim.x)                // pair index C(b,2) + a
-            for (int a = 0; a < b; a++) s_pair[b * (b - 1) / 2 + a] = (uint16_t)(a | b << 8);
         __syncthreads();
 
         unsigned long long win = 0, tie = 0, lose = 0;

@@ -484,10 +484,11 @@ def test_one_query_fast_path_equals_the_batched_path(torch_mod):
                 assert one["wins"] + one["ties"] <= runs
 
 
-def test_sync_free_mixed_batches_equal_the_classified_path(torch_mod):
-    """npk_equity_batch_async sorts a mixed batch by shape on the device and enqueues one kernel per shape of the mask
-    without any host round trip: same counters as the path that reads the shape counts back, in both dealing modes;
-    queries whose shape is not in the mask are left untouched."""
+def test_mixed_kernel_equals_the_per_shape_kernels(torch_mod):
+    """A mixed batch runs through ONE persistent kernel for all shapes (csrc/npk_mixed.cu, via npk_equity_batch and via
+    npk_equity_batch_async with a shape mask): same counters, win types and passes as the shape-specialised kernels give query
+    by query (uniform_shape hint, the query's own number in the Philox counter), in both dealing modes; queries whose shape is
+    not in the mask are left untouched."""
     import neuron_poker_b200 as npk
     from neuron_poker_b200.equity import shape_mask
     rng = np.random.default_rng(11)
@@ -505,6 +506,13 @@ def test_sync_free_mixed_batches_equal_the_classified_path(torch_mod):
                                  trial_offset=3, query_offset=9, shapes=shape_mask(range(1, 8)))
         for k in ("wins", "ties", "win_types") + (("passes",) if mode == "reference" else ()):
             assert (a[k] == b[k]).all(), (mode, k)
+        for q in range(Q):
+            known = int((board[q] != NO).sum())
+            one = npk.get_equity_batch(hole[q:q + 1], board[q:q + 1], npl[q:q + 1], 777, seed_value=21, deal_mode=mode,
+                                       win_types=True, passes=(mode == "reference"), trial_offset=3, query_offset=9 + q,
+                                       uniform_shape=(int(npl[q]), known), validate=False)
+            for k in ("wins", "ties", "win_types") + (("passes",) if mode == "reference" else ()):
+                assert (one[k][0] == a[k][q]).all(), (mode, k, q, int(npl[q]), known)
         c = npk.get_equity_batch(hole, board, npl, 777, seed_value=21, deal_mode=mode, shapes=shape_mask([2, 3]),
                                  trial_offset=3, query_offset=9)
         sel = torch_mod.as_tensor((npl == 2) | (npl == 3)).to(c["wins"].device)
