@@ -510,6 +510,31 @@ def run_latency(args, wl, cx, with_cpu):
     vals = [fn() for _ in range(n)]
     dt = time.perf_counter() - t0
     res["get_equity_6_players_flop"] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt, "mean_equity": sum(vals) / n}
+    # the same call from several host threads at once (the host entry point is re-entrant: every thread owns its stream and
+    # result block inside libnpk, ctypes releases the GIL during the call): aggregate calls/s of the process
+    import threading
+    for nt in (2, 4):
+        n_each = 1500
+        gate = threading.Barrier(nt + 1)
+
+        def worker():
+            for _ in range(30):
+                fn()
+            gate.wait()
+            for _ in range(n_each):
+                fn()
+            gate.wait()
+
+        ts = [threading.Thread(target=worker) for _ in range(nt)]
+        for t in ts:
+            t.start()
+        gate.wait()
+        t0 = time.perf_counter()
+        gate.wait()
+        dt = time.perf_counter() - t0
+        for t in ts:
+            t.join()
+        res["get_equity_6_players_flop"]["calls_per_s_%d_host_threads" % nt] = nt * n_each / dt
     if with_cpu:
         try:
             from oracle import ref_python
@@ -604,8 +629,11 @@ def run_mc(args, wl, cx, deal, steps, warmup, peak=None, peak_detail=None, e2e=T
                             "nominal_issue_peak": 148 * 128 * 1.965e9 / 1e12}
     if e2e:
         # end to end through the host-buffer API: queries in host memory, counters back in host memory, every step
-        e2e_steps = max(3, min(steps, 20))
-        for i in range(2):
+        # (for query-sharded workloads: two batches in flight per rank -- submit batch i+1, then collect batch i -- so the
+        # staging and the copies overlap the previous kernel; every step still copies its queries H2D from pinned staging
+        # and its counters D2H inside the timed region; the blocking one-call-per-step figure is reported next to it)
+        e2e_steps = max(3, min(steps, 100))
+        for i in range(5):                                # every staging slot of the library allocated before the clock starts
             npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5000 + i, deal_mode=deal)
         cx.barrier()
         pinned = [torch.as_tensor(x).pin_memory() for x in (hole_h, board_h, npl_h)]
@@ -623,6 +651,27 @@ def run_mc(args, wl, cx, deal, steps, warmup, peak=None, peak_detail=None, e2e=T
                        "d2h_bytes_per_step": int(16 * Q), "steps": e2e_steps,
                        "api": ("pinned host queries -> TrialShardedJob.step (trial shard + count reduction) -> host" if by_trial
                                else "neuron_poker_b200.equity_counts_batch -> npk_equity_host")}
+        if not by_trial:
+            for w in [npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=5100 + i, deal_mode=deal, block=False)
+                      for i in range(npk.equity.MAX_IN_FLIGHT)]:
+                w.result()                                # every staging slot allocated before the clock starts
+            cx.barrier()
+            pend, check = [], None
+            e0 = time.perf_counter()
+            for i in range(e2e_steps):
+                pend.append(npk.equity_counts_batch(hole_h, board_h, npl_h, t_cnt, seed_value=6000 + i, deal_mode=deal,
+                                                    block=False))
+                if len(pend) > 1:
+                    check = pend.pop(0).result()
+            while pend:
+                check = pend.pop(0).result()
+            piped_s = cx.max_over_ranks(time.perf_counter() - e0)
+            assert (check["wins"] == r["wins"]).all() and (check["ties"] == r["ties"]).all()     # same seed as the last blocking step
+            line["e2e"].update({"blocking_value": line["e2e"]["value"], "value": Q * t_cnt * P * world * e2e_steps / piped_s,
+                                "in_flight": 2,
+                                "api": "neuron_poker_b200.equity_counts_batch(block=False) -> npk_equity_host_submit / "
+                                       "npk_equity_host_wait, two batches in flight; blocking_value = one blocking "
+                                       "npk_equity_host call per step"})
     return line, (hole_h, board_h, npl_h)
 
 

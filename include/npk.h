@@ -149,6 +149,21 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
                     uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                     uint64_t* passes);
 
+/* HOST, pipelined: the two halves of npk_equity_host, so that a caller can keep several batches in flight -- the host-side
+ * staging and the copies of batch i+1 overlap the kernel of batch i (each batch in flight owns pinned staging, device buffers
+ * and a stream inside the library; kernels of consecutive batches fill each other's tails).
+ *   npk_equity_host_submit  validates and stages the batch, enqueues H2D copy + kernels + D2H copy and returns a ticket >= 0
+ *                           without waiting for the device (a negative NPK_ERR_* code on failure).  want bit 0: win types,
+ *                           bit 1: passes.  At most NPK_HOST_SLOTS tickets per host thread may be outstanding.
+ *   npk_equity_host_wait    blocks until that batch has finished and copies its counters out (same meaning as
+ *                           npk_equity_host's outputs; win_types / passes may be NULL).  A ticket belongs to the thread that
+ *                           submitted it and can be waited for once; tickets may be waited for in any order.
+ * Results are bit-identical to npk_equity_host with the same arguments. */
+#define NPK_HOST_SLOTS 4
+int64_t npk_equity_host_submit(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                               uint64_t seed, int deal_mode, uint32_t want);
+int npk_equity_host_wait(int64_t ticket, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes);
+
 /* HOST, blocking: ONE query with as few arguments as a foreign-function call can have -- what the Python drop-in's get_equity
  * (montecarlo_python.py:401-406) calls.  packed = hole[0] | hole[1] << 8 | board[0] << 16 | ... | board[4] << 48 (card ids,
  * 0xFF = no card, known cards first); want bit 0: win types, bit 1: passes; out[12] (host) = wins, ties, win types[9],

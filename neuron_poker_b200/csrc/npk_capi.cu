@@ -37,8 +37,9 @@ DeviceState g_dev[kMaxDevices];
 
 // host-staging state of npk_equity_host: one per CALLING THREAD (its own stream, pinned buffers and one-query scratch), so
 // the host entry point is re-entrant -- two host threads never share a stream, a counter or a result block
-struct HostStage {
-    int device = -1;
+// One batch in flight through the host entry points: its own pinned staging, device buffers, workspace, stream and "done"
+// event, so that the copies and the host-side work of batch i+1 overlap the kernel of batch i (npk_equity_host_submit / _wait).
+struct HostSlot {
     int64_t cap_q = 0;
     uint8_t* h_in = nullptr;      // pinned: hole[2Q] board[5Q] players[Q]
     uint64_t* h_out = nullptr;    // pinned: wins[Q] ties[Q] types[9Q] passes[Q]
@@ -46,6 +47,25 @@ struct HostStage {
     uint64_t* d_out = nullptr;
     void* d_ws = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    int64_t ticket = -1;          // -1: free
+    int64_t Q = 0;
+    uint32_t want = 0;            // bit 0: win types, bit 1: passes
+    void free_buffers()
+    {
+        cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
+        h_in = nullptr; h_out = nullptr; d_in = nullptr; d_out = nullptr; d_ws = nullptr; cap_q = 0;
+    }
+};
+constexpr int kHostSlots = NPK_HOST_SLOTS;
+
+// host-staging state of the host entry points: one per CALLING THREAD (its own streams, pinned buffers and one-query scratch),
+// so they are re-entrant -- two host threads never share a stream, a counter or a result block
+struct HostStage {
+    int device = -1;
+    HostSlot slot[kHostSlots];
+    int64_t next_ticket = 0;
+    cudaStream_t stream = nullptr;       // the one-query path
     // one-query blocking calls (Q == 1): counters in device memory, results in mapped host memory
     npk::SingleCall* single = nullptr;
     npk::SingleResult* single_host = nullptr;
@@ -56,7 +76,12 @@ struct HostStage {
         int cur = -1;
         if (cudaGetDevice(&cur) != cudaSuccess) { device = -1; return; }     // runtime already torn down
         cudaSetDevice(device);
-        cudaFreeHost(h_in); cudaFreeHost(h_out); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
+        for (HostSlot& s : slot) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.free_buffers();
+            if (s.done) cudaEventDestroy(s.done);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
         cudaFree(single); cudaFreeHost(single_host);
         if (stream) cudaStreamDestroy(stream);
         if (cur >= 0) cudaSetDevice(cur);
@@ -619,41 +644,37 @@ int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint
 }
 }  // namespace
 
-int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
-                    uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
-                    uint64_t* passes)
+namespace {
+// this thread's staging on the current device (created on first use, rebuilt when the thread switches devices)
+int thread_stage(HostStage** out)
 {
-    DeviceState* ds;
-    int rc = current_state(&ds);
-    if (rc) return rc;
-    if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
-    if (!hole || !board || !n_players || !wins_strict || !ties) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
     int dev = 0;
     cudaGetDevice(&dev);
-    HostStage& st = t_stage;                       // this thread's staging: no lock, no shared stream
+    HostStage& st = t_stage;                       // no lock, no shared stream
     if (st.device != dev) st.release();
-    cudaError_t e;
     if (st.device < 0) {
-        if ((e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        cudaError_t e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return cuda_fail(e, "stream");
         st.device = dev;
     }
-    if (Q == 1 && !tuning().no_single_path)
-        return single_query(ds, st, hole, board, n_players[0], trials, seed, deal_mode, wins_strict, ties, win_types, passes);
-    if (st.cap_q < Q) {
-        cudaFreeHost(st.h_in); cudaFreeHost(st.h_out); cudaFree(st.d_in); cudaFree(st.d_out); cudaFree(st.d_ws);
-        st.h_in = nullptr; st.h_out = nullptr; st.d_in = nullptr; st.d_out = nullptr; st.d_ws = nullptr; st.cap_q = 0;
-        const int64_t cap = Q < 1024 ? 1024 : Q;
-        if ((e = cudaMallocHost(&st.h_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-        if ((e = cudaMallocHost(&st.h_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-        if ((e = cudaMalloc(&st.d_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&st.d_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        if ((e = cudaMalloc(&st.d_ws, npk_equity_workspace_bytes(cap))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-        st.cap_q = cap;
-    }
-    std::memcpy(st.h_in, hole, 2 * Q);
-    std::memcpy(st.h_in + 2 * Q, board, 5 * Q);
-    std::memcpy(st.h_in + 7 * Q, n_players, Q);
-    // a uniform shape lets the call run without the classification round trip; validate on the host instead
+    *out = &st;
+    return NPK_OK;
+}
+
+// Validate a batch on the host, stage it in the next slot and enqueue H2D copy + counter reset + kernels + D2H copy on that
+// slot's stream.  Nothing waits for the device here.
+int host_submit(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q,
+                int64_t trials, uint64_t seed, int deal_mode, uint32_t want, int64_t* ticket)
+{
+    (void)ds;
+    int free_slot = -1;
+    for (int i = 0; i < kHostSlots && free_slot < 0; i++)
+        if (st.slot[i].ticket < 0) free_slot = i;
+    HostSlot& sl = st.slot[free_slot < 0 ? 0 : free_slot];
+    if (free_slot < 0)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "npk_equity_host_submit: NPK_HOST_SLOTS batches are already in flight on this "
+                                              "thread; wait for one of them first");
+    // a uniform shape lets the call run without the classification pass; validate on the host instead
     int up = n_players[0], uk = 0;
     for (int i = 0; i < 5; i++) uk += board[i] != 0xFF;
     bool uniform = true;
@@ -677,25 +698,108 @@ int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_
                              ": card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
         if (n_players[q] != up || known != uk) uniform = false;
     }
-    const size_t n_out = (size_t)Q * 12;
-    if ((e = cudaMemcpyAsync(st.d_in, st.h_in, 8 * Q, cudaMemcpyHostToDevice, st.stream)) != cudaSuccess) return cuda_fail(e, "H2D");
-    if ((e = cudaMemsetAsync(st.d_out, 0, 8 * n_out, st.stream)) != cudaSuccess) return cuda_fail(e, "memset");
-    uint64_t* d_wins = st.d_out;
-    uint64_t* d_ties = st.d_out + Q;
-    uint64_t* d_types = st.d_out + 2 * Q;
-    uint64_t* d_pass = st.d_out + 11 * Q;
-    rc = npk_equity_batch(st.d_in, st.d_in + 2 * Q, st.d_in + 7 * Q, Q, trials, uniform ? up : -1, uniform ? uk : -1, seed,
-                          0, 0, deal_mode, 0, d_wins, d_ties, win_types ? d_types : nullptr, passes ? d_pass : nullptr,
-                          st.d_ws, st.stream);
+    cudaError_t e;
+    if (!sl.stream) {
+        if ((e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "stream");
+        if ((e = cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event");
+    }
+    if (sl.cap_q < Q) {
+        sl.free_buffers();
+        const int64_t cap = Q < 1024 ? 1024 : Q;
+        if ((e = cudaMallocHost(&sl.h_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        if ((e = cudaMallocHost(&sl.h_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+        if ((e = cudaMalloc(&sl.d_in, 8 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&sl.d_out, 8 * 12 * cap)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc(&sl.d_ws, npk_equity_workspace_bytes(cap))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        sl.cap_q = cap;
+    }
+    std::memcpy(sl.h_in, hole, 2 * Q);
+    std::memcpy(sl.h_in + 2 * Q, board, 5 * Q);
+    std::memcpy(sl.h_in + 7 * Q, n_players, Q);
+    const bool types = want & 1u, pass = want & 2u;
+    const size_t n_out = (size_t)Q * (pass ? 12 : (types ? 11 : 2));
+    if ((e = cudaMemcpyAsync(sl.d_in, sl.h_in, 8 * Q, cudaMemcpyHostToDevice, sl.stream)) != cudaSuccess) return cuda_fail(e, "H2D");
+    if ((e = cudaMemsetAsync(sl.d_out, 0, 8 * n_out, sl.stream)) != cudaSuccess) return cuda_fail(e, "memset");
+    uint64_t* d_wins = sl.d_out;
+    uint64_t* d_ties = sl.d_out + Q;
+    uint64_t* d_types = sl.d_out + 2 * Q;
+    uint64_t* d_pass = sl.d_out + 11 * Q;
+    int rc = npk_equity_batch(sl.d_in, sl.d_in + 2 * Q, sl.d_in + 7 * Q, Q, trials, uniform ? up : -1, uniform ? uk : -1, seed,
+                              0, 0, deal_mode, 0, d_wins, d_ties, types ? d_types : nullptr, pass ? d_pass : nullptr,
+                              sl.d_ws, sl.stream);
     if (rc) return rc;
-    const size_t n_copy = passes ? 12 * Q : (win_types ? 11 * Q : 2 * Q);
-    if ((e = cudaMemcpyAsync(st.h_out, st.d_out, 8 * n_copy, cudaMemcpyDeviceToHost, st.stream)) != cudaSuccess) return cuda_fail(e, "D2H");
-    if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernels");
-    std::memcpy(wins_strict, st.h_out, 8 * Q);
-    std::memcpy(ties, st.h_out + Q, 8 * Q);
-    if (win_types) std::memcpy(win_types, st.h_out + 2 * Q, 8 * 9 * Q);
-    if (passes) std::memcpy(passes, st.h_out + 11 * Q, 8 * Q);
+    if ((e = cudaMemcpyAsync(sl.h_out, sl.d_out, 8 * n_out, cudaMemcpyDeviceToHost, sl.stream)) != cudaSuccess) return cuda_fail(e, "D2H");
+    if ((e = cudaEventRecord(sl.done, sl.stream)) != cudaSuccess) return cuda_fail(e, "event record");
+    sl.Q = Q;
+    sl.want = want;
+    sl.ticket = (st.next_ticket++) * kHostSlots + free_slot;      // ticket % NPK_HOST_SLOTS = its slot
+    *ticket = sl.ticket;
     return NPK_OK;
+}
+
+int host_wait(HostStage& st, int64_t ticket, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+{
+    if (ticket < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "npk_equity_host_wait: bad ticket");
+    HostSlot& sl = st.slot[ticket % kHostSlots];
+    if (sl.ticket != ticket)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "npk_equity_host_wait: no such batch in flight on this thread (tickets belong to "
+                                              "the submitting thread and can be waited for once)");
+    cudaError_t e = cudaEventSynchronize(sl.done);
+    sl.ticket = -1;
+    if (e != cudaSuccess) return cuda_fail(e, "equity kernels");
+    const int64_t Q = sl.Q;
+    if (wins_strict) std::memcpy(wins_strict, sl.h_out, 8 * Q);
+    if (ties) std::memcpy(ties, sl.h_out + Q, 8 * Q);
+    if (win_types && (sl.want & 1u)) std::memcpy(win_types, sl.h_out + 2 * Q, 8 * 9 * Q);
+    if (passes && (sl.want & 2u)) std::memcpy(passes, sl.h_out + 11 * Q, 8 * Q);
+    return NPK_OK;
+}
+}  // namespace
+
+int npk_equity_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                    uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
+                    uint64_t* passes)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q <= 0) return Q == 0 ? NPK_OK : fail(NPK_ERR_INVALID_ARGUMENT, "negative Q");
+    if (!hole || !board || !n_players || !wins_strict || !ties) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    HostStage* st;
+    if ((rc = thread_stage(&st))) return rc;
+    if (Q == 1 && !tuning().no_single_path)
+        return single_query(ds, *st, hole, board, n_players[0], trials, seed, deal_mode, wins_strict, ties, win_types, passes);
+    int64_t ticket = -1;
+    rc = host_submit(ds, *st, hole, board, n_players, Q, trials, seed, deal_mode, (win_types ? 1u : 0u) | (passes ? 2u : 0u),
+                     &ticket);
+    if (rc) return rc;
+    return host_wait(*st, ticket, wins_strict, ties, win_types, passes);
+}
+
+int64_t npk_equity_host_submit(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, int64_t Q, int64_t trials,
+                               uint64_t seed, int deal_mode, uint32_t want)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    if (Q <= 0) return fail(NPK_ERR_INVALID_ARGUMENT, "npk_equity_host_submit: Q must be positive");
+    if (!hole || !board || !n_players) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    HostStage* st;
+    if ((rc = thread_stage(&st))) return rc;
+    int64_t ticket = -1;
+    rc = host_submit(ds, *st, hole, board, n_players, Q, trials, seed, deal_mode, want, &ticket);
+    return rc ? rc : ticket;
+}
+
+int npk_equity_host_wait(int64_t ticket, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    HostStage* st;
+    if ((rc = thread_stage(&st))) return rc;
+    return host_wait(*st, ticket, wins_strict, ties, win_types, passes);
 }
 
 /* One query from the host with as few arguments as a foreign-function call can have (the Python drop-in's get_equity):
@@ -708,15 +812,9 @@ int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, 
     if (!out) return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
     uint8_t q[7];
     for (int i = 0; i < 7; i++) q[i] = (uint8_t)(packed >> (8 * i));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    HostStage& st = t_stage;
-    if (st.device != dev) st.release();
-    if (st.device < 0) {
-        cudaError_t e = cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) return cuda_fail(e, "stream");
-        st.device = dev;
-    }
+    HostStage* stp;
+    if ((rc = thread_stage(&stp))) return rc;
+    HostStage& st = *stp;
     const uint8_t np = (uint8_t)(players < 0 || players > 255 ? 255 : players);
     if (tuning().no_single_path)
         return npk_equity_host(q, q + 2, &np, 1, trials, seed, deal_mode, out, out + 1, (want & 1u) ? out + 2 : nullptr,

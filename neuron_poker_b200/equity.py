@@ -127,11 +127,34 @@ def equity_counts(player_cards, table_cards, players, runs, deal_mode="uniform",
     return res
 
 
+class PendingCounts(object):
+    """A batch in flight (equity_counts_batch(..., block=False)): result() blocks until its counters are on the host."""
+
+    def __init__(self, L, ticket, out):
+        self._L, self._ticket, self._out = L, ticket, out
+
+    def result(self):
+        if self._ticket is not None:
+            out = self._out
+            rc = self._L.npk_equity_host_wait(self._ticket, _u8(out["wins"]), _u8(out["ties"]),
+                                              _u8(out["win_types"]) if "win_types" in out else None,
+                                              _u8(out["passes"]) if "passes" in out else None)
+            self._ticket = None
+            _lib.check(rc)
+        return self._out
+
+
+MAX_IN_FLIGHT = 4          # NPK_HOST_SLOTS
+
+
 def equity_counts_batch(hole, board, n_players, trials, seed_value=0, deal_mode="uniform", win_types=False,
-                        passes=False):
+                        passes=False, block=True):
     """Host arrays in, host arrays out (numpy, uint8 [Q,2] / [Q,5] with 0xFF padding / [Q]): one blocking call of
     npk_equity_host = H2D copy of the queries from pinned staging, the kernels, D2H copy of the counters.
-    Returns dict(wins [Q] uint64, ties [Q] uint64[, win_types [Q,9], passes [Q]])."""
+    Returns dict(wins [Q] uint64, ties [Q] uint64[, win_types [Q,9], passes [Q]]).
+    block=False submits the batch (npk_equity_host_submit) and returns a PendingCounts whose result() gives the same dict:
+    up to MAX_IN_FLIGHT batches per thread can be in flight, so the staging and the copies of one batch overlap the kernel
+    of the previous one (the queries are copied at submission; the arrays may be reused at once)."""
     hole = np.ascontiguousarray(hole, dtype=np.uint8).reshape(-1, 2)
     board = np.ascontiguousarray(board, dtype=np.uint8).reshape(-1, 5)
     n_players = np.ascontiguousarray(n_players, dtype=np.uint8).reshape(-1)
@@ -144,6 +167,14 @@ def equity_counts_batch(hole, board, n_players, trials, seed_value=0, deal_mode=
         out["win_types"] = np.zeros((Q, 9), dtype=np.uint64)
     if passes:
         out["passes"] = np.zeros(Q, dtype=np.uint64)
+    if not block:
+        if Q == 0:
+            return PendingCounts(L, None, out)
+        ticket = L.npk_equity_host_submit(_u8(hole), _u8(board), _u8(n_players), Q, int(trials),
+                                          ctypes.c_uint64(int(seed_value) & (2**64 - 1)), _DEAL[deal_mode],
+                                          (1 if win_types else 0) | (2 if passes else 0))
+        _lib.check(ticket)
+        return PendingCounts(L, ticket, out)
     _lib.check(L.npk_equity_host(_u8(hole), _u8(board), _u8(n_players), Q, int(trials),
                                  ctypes.c_uint64(int(seed_value) & (2**64 - 1)), _DEAL[deal_mode], _u8(out["wins"]),
                                  _u8(out["ties"]), _u8(out["win_types"]) if win_types else None,

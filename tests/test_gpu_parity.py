@@ -561,3 +561,55 @@ def test_host_entry_points_are_reentrant(torch_mod):
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+def test_pipelined_host_batches_equal_blocking_calls(torch_mod):
+    """npk_equity_host_submit / npk_equity_host_wait (equity_counts_batch(block=False)): batches kept in flight give exactly
+    the counters of the blocking call with the same arguments -- uniform-shape and mixed batches, both dealers, win types and
+    passes, collected out of order; a fifth outstanding ticket, a ticket waited for twice and bad cards are errors."""
+    from neuron_poker_b200._lib import NpkError
+    rng = np.random.default_rng(21)
+    jobs = []
+    for k in range(7):
+        Q = int(rng.integers(3, 400))
+        cards = np.stack([rng.permutation(52)[:7] for _ in range(Q)]).astype(np.uint8)
+        known = rng.choice([0, 3, 4, 5], size=Q) if k % 2 else np.full(Q, [3, 0, 4, 5][k // 2 % 4])
+        board = cards[:, 2:].copy()
+        for q in range(Q):
+            board[q, known[q]:] = NO
+        npl = rng.integers(2, 8, size=Q).astype(np.uint8) if k % 2 else np.full(Q, 2 + k, dtype=np.uint8)
+        mode = "reference" if k % 3 == 0 else "uniform"
+        kw = dict(seed_value=300 + k, deal_mode=mode, win_types=k % 2 == 0, passes=(mode == "reference"))
+        jobs.append((cards[:, :2].copy(), board, npl, 500 + 37 * k, kw))
+    want = [npk.equity_counts_batch(h, b, n, t, **kw) for h, b, n, t, kw in jobs]
+    pend, got = [], {}
+    for i, (h, b, n, t, kw) in enumerate(jobs):
+        pend.append((i, npk.equity_counts_batch(h, b, n, t, block=False, **kw)))
+        h[:] = 0                                     # the queries were copied at submission
+        if len(pend) == npk.equity.MAX_IN_FLIGHT:
+            j, p = pend.pop(1)                       # out of order
+            got[j] = p.result()
+    for j, p in pend:
+        got[j] = p.result()
+    for i, w in enumerate(want):
+        assert set(got[i]) == set(w)
+        for k in w:
+            assert (got[i][k] == w[k]).all(), (i, k)
+    h, b, n, t, kw = jobs[1]
+    h[:] = 5                                         # the same card twice: rejected at submission
+    with pytest.raises(NpkError):
+        npk.equity_counts_batch(h, b, n, t, block=False)
+    h2, b2, n2, t2, kw2 = jobs[2]
+    h2[:] = 50
+    h2[:, 1] = 51
+    b2[:] = NO
+    many = [npk.equity_counts_batch(h2, b2, n2, 64, block=False) for _ in range(npk.equity.MAX_IN_FLIGHT)]
+    with pytest.raises(NpkError):
+        npk.equity_counts_batch(h2, b2, n2, 64, block=False)
+    first = many[0].result()
+    again = npk.equity_counts_batch(h2, b2, n2, 64, block=False)        # a slot is free again
+    for p in many[1:] + [again]:
+        r = p.result()
+        assert (r["wins"] == first["wins"]).all()
+    L = npk._lib.lib()
+    assert L.npk_equity_host_wait(10**6, None, None, None, None) < 0
