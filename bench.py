@@ -510,6 +510,29 @@ def run_latency(args, wl, cx, with_cpu):
     vals = [fn() for _ in range(n)]
     dt = time.perf_counter() - t0
     res["get_equity_6_players_flop"] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt, "mean_equity": sum(vals) / n}
+    # resident mode (opt-in, npk_resident_start): a persistent kernel serves the calls from a mailbox in mapped host memory,
+    # no kernel launch per call; same results bit for bit
+    npk.resident(True, idle_us=1000)
+    try:
+        for _ in range(30):
+            fn()
+        n = 2000
+        t0 = time.perf_counter()
+        vals = [fn() for _ in range(n)]
+        dt = time.perf_counter() - t0
+        res["get_equity_6_players_flop"]["resident"] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt,
+                                                        "mean_equity": sum(vals) / n, "calls": n,
+                                                        "mode": "neuron_poker_b200.resident(True): persistent server kernel on all "
+                                                                "SMs, idle limit 1 ms"}
+        f1 = lambda: npk.get_equity({"AS", "KS"}, set(), 2, 10000)      # noqa: E731
+        for _ in range(30):
+            f1()
+        t0 = time.perf_counter()
+        vals = [f1() for _ in range(n)]
+        dt = time.perf_counter() - t0
+        res["get_equity"]["resident"] = {"us_per_call": 1e6 * dt / n, "calls_per_s": n / dt, "mean_equity": sum(vals) / n}
+    finally:
+        npk.resident(False)
     # the same call from several host threads at once (the host entry point is re-entrant: every thread owns its stream and
     # result block inside libnpk, ctypes releases the GIL during the call): aggregate calls/s of the process
     import threading
@@ -833,6 +856,7 @@ def main():
     extras = {}
     lat = run_latency(args, workload("cfg1"), cx, with_cpu) if rank == 0 else None
     line["get_equity_calls_per_s"] = lat["get_equity_6_players_flop"]["calls_per_s"] if lat else None
+    line["get_equity_calls_per_s_resident_mode"] = lat["get_equity_6_players_flop"]["resident"]["calls_per_s"] if lat else None
     extras["cfg1"] = lat
     cx.barrier()
 

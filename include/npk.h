@@ -171,6 +171,19 @@ int npk_equity_host_wait(int64_t ticket, uint64_t* wins_strict, uint64_t* ties, 
  * sequence number in mapped host memory; the host spins on the number).  Validated like npk_equity_host. */
 int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, int deal_mode, uint32_t want, uint64_t* out);
 
+/* HOST.  Resident mode of the one-query path, per calling thread, opt-in.  npk_resident_start launches a persistent kernel on
+ * `ctas` SMs (<= 0: all of them) that keeps the rank tables staged in shared memory and serves this thread's npk_equity_one /
+ * one-query npk_equity_host calls (wins and ties only, fewer than 2^32 trials) out of a mailbox in mapped host memory: the call
+ * posts the query (two 16-byte records), the kernel's polling thread picks it up over PCIe, the warps of all its CTAs run the
+ * trials and the last CTA stores wins, ties and the call's sequence number back with one 16-byte store -- no kernel launch, no
+ * CUDA call per query.  Results are bit-identical to the launch-per-call path (same Philox streams).
+ * The kernel leaves on its own when no query has arrived for `idle_us` microseconds (<= 0: 200; at most 100,000) and is
+ * started again by the next query, so it never holds the device for longer than that on its own; while it is resident, other
+ * work submitted to the device waits for the SMs it occupies (libnpk's own host entry points of this thread stop it first).
+ * npk_resident_stop makes the thread's calls launch a kernel per call again.  Both synchronise with the server only. */
+int npk_resident_start(int ctas, int idle_us);
+int npk_resident_stop(void);
+
 /*
  * Monte-Carlo equity with RANGES (run_montecarlo's opponent_range / set-typed player cards / ghost_cards).
  * A starting-hand class is an unordered rank pair plus suitedness, numbered  suited hi*13+lo,  offsuit and pairs

@@ -13,7 +13,7 @@ All compute runs in libnpk.so's CUDA kernels; importing this package does not im
 from .cards import CARD_RANKS_ORIGINAL, SUITS_ORIGINAL, HAND_TYPES, card_id, card_str  # noqa: F401
 from .equity import (DEAL_REFERENCE, DEAL_UNIFORM, MonteCarlo, equity_counts, equity_counts_batch,  # noqa: F401
                      equity_counts_ranges, get_equity, get_equity_batch, get_equity_ranges_batch, montecarlo,
-                     numpy_montecarlo, seed)
+                     numpy_montecarlo, resident, seed)
 from . import dist, holdem, ranges  # noqa: F401
 from .evaluator import (enumerate_equity, eval_best_hand, get_winner, host_rank7, host_tables, rank7, rank7_colex,  # noqa: F401
                         showdown)

@@ -53,6 +53,7 @@ def lib():
                 L.npk_equity_host_submit.argtypes = [u8, u8, u8, i64, i64, ctypes.c_uint64, i32, ctypes.c_uint32]
                 L.npk_equity_host_submit.restype = i64
                 L.npk_equity_host_wait.argtypes = [i64, u64, u64, u64, u64]
+                L.npk_resident_start.argtypes = [i32, i32]
                 L.npk_equity_one.argtypes = [ctypes.c_uint64, i32, i64, ctypes.c_uint64, i32, ctypes.c_uint32, u64]
                 L.npk_equity_ranges_batch.argtypes = [u8, u8, u8, u8, i64, i64, u64, u64, ctypes.c_uint64, i64, i64, i32,
                                                       ctypes.c_uint32, u64, u64, u64, u64, vp, vp]

@@ -26,6 +26,7 @@ std::mutex g_mu;
 struct DeviceState {
     bool ready = false;
     int sm_count = 0;
+    int clock_khz = 0;
     npk::DeviceTables t{};
     void* blob = nullptr;
 };
@@ -70,12 +71,24 @@ struct HostStage {
     npk::SingleCall* single = nullptr;
     npk::SingleResult* single_host = nullptr;
     unsigned long long single_seq = 0;
+    // resident mode of the one-query path (npk_resident_start): a persistent kernel serves this thread's calls from a mailbox
+    bool res_enabled = false, res_running = false;
+    int res_ctas = 0;
+    long long res_idle_cycles = 0;
+    npk::ResidentMailbox* res_mb = nullptr;       // mapped host memory
+    npk::ResidentMailbox* res_mb_dev = nullptr;   // the same block as the device sees it
+    npk::ResidentState* res_state = nullptr;      // device memory
+    unsigned long long res_launch_id = 0;
+    unsigned int res_seq = 0;
+    void stop_resident();
     void release()
     {
         if (device < 0) return;
         int cur = -1;
         if (cudaGetDevice(&cur) != cudaSuccess) { device = -1; return; }     // runtime already torn down
         cudaSetDevice(device);
+        stop_resident();
+        cudaFree(res_state); cudaFreeHost(res_mb);
         for (HostSlot& s : slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.free_buffers();
@@ -90,6 +103,22 @@ struct HostStage {
     ~HostStage() { release(); }
 };
 thread_local HostStage t_stage;
+
+// Ask this thread's resident server to leave and wait until it has (it polls the mailbox every couple of microseconds).
+void HostStage::stop_resident()
+{
+    if (!res_running || !res_mb) { res_running = false; return; }
+    volatile npk::ResidentMailbox* mb = res_mb;
+    mb->b.stop = (unsigned int)res_launch_id;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    for (long spins = 0; spins < 20000000 && mb->exited != res_launch_id; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    cudaStreamSynchronize(stream);            // the kernel itself has ended (bounded by its idle limit in any case)
+    res_running = false;
+}
 
 // Tuning aids, read from the environment ONCE (a getenv per launch costs as much as the launch of a 30 us call).
 struct Tuning {
@@ -311,6 +340,7 @@ int npk_init(int device)
         return fail(NPK_ERR_CUDA, "libnpk is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
                                       std::to_string(prop.minor));
     ds.sm_count = prop.multiProcessorCount;
+    if (cudaDeviceGetAttribute(&ds.clock_khz, cudaDevAttrClockRate, device) != cudaSuccess || ds.clock_khz <= 0) ds.clock_khz = 2000000;
 
     const size_t vb = (g_tables.value.size() * 2 + 15) & ~size_t(15);
     const size_t rb = g_tables.row_offset.size() * 2, fb = g_tables.flush.size() * 2, db = 52 * 4;
@@ -561,14 +591,9 @@ int npk_equity_batch_status(const void* workspace, void* stream, uint32_t* inval
 }
 
 namespace {
-// One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in device memory
-// between calls (the last warp hands them over and zeroes them), the result lands in mapped host memory together with the
-// call's sequence number, and the host spins on that number instead of asking the driver to synchronise the stream.
-// No H2D / D2H copy, no memset, no cudaStreamSynchronize on the fast path.
-int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, int players, int64_t trials,
-                 uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+// validation of one host query (what npk_equity_host does per query); returns the number of known board cards or -1
+int validate_one(const uint8_t* hole, const uint8_t* board, int players)
 {
-    cudaError_t e;
     unsigned long long mask = 0;
     int known = 0;
     bool ended = false, bad = players < 1 || players > 10;
@@ -583,10 +608,97 @@ int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint
         mask |= 1ull << c;
         known++;
     }
-    if (bad) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+    return bad ? -1 : known;
+}
+
+// (Re)start this thread's resident server on its stream.  `completed` = sequence number of the last request whose result has
+// been received: a request posted after it is picked up by the new server at its first poll.
+int resident_launch(DeviceState* ds, HostStage& st)
+{
+    cudaError_t e;
+    if (!st.res_mb) {
+        if ((e = cudaHostAlloc(&st.res_mb, sizeof(npk::ResidentMailbox), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+        std::memset(st.res_mb, 0, sizeof(npk::ResidentMailbox));
+        if ((e = cudaHostGetDevicePointer(&st.res_mb_dev, st.res_mb, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+        if ((e = cudaMalloc(&st.res_state, sizeof(npk::ResidentState))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    }
+    if ((e = cudaMemsetAsync(st.res_state, 0, sizeof(npk::ResidentState), st.stream)) != cudaSuccess) return cuda_fail(e, "memset");
+    const unsigned int completed = (unsigned int)const_cast<volatile npk::ResidentMailbox*>(st.res_mb)->done.seq;
+    ++st.res_launch_id;
+    e = npk::launch_equity_resident(ds->t, st.res_state, st.res_mb_dev, st.res_launch_id, completed, st.res_idle_cycles,
+                                    st.res_ctas, st.stream);
+    if (e != cudaSuccess) return cuda_fail(e, "resident kernel launch");
+    st.res_running = true;
+    return NPK_OK;
+}
+
+// One query through the resident server: post the request in the mailbox, spin on the result.  No CUDA call on this path
+// unless the server has left in the meantime (idle limit) and is started again.
+int resident_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, int players, int64_t trials,
+                   uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties)
+{
+    if (validate_one(hole, board, players) < 0)
+        return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+    wins_strict[0] = 0; ties[0] = 0;
+    if (trials == 0) return NPK_OK;
+    if (!st.res_mb) { int rc = resident_launch(ds, st); if (rc) return rc; }
+    volatile npk::ResidentMailbox* mb = st.res_mb;
+    unsigned int seq = ++st.res_seq;
+    if (seq == 0) seq = ++st.res_seq;
+    const unsigned int packed_lo = (unsigned int)hole[0] | (unsigned int)hole[1] << 8 | (unsigned int)board[0] << 16 |
+                                   (unsigned int)board[1] << 24;
+    const unsigned int packed_hi = (unsigned int)board[2] | (unsigned int)board[3] << 8 | (unsigned int)board[4] << 16 |
+                                   (unsigned int)players << 24 | (deal_mode == NPK_DEAL_REFERENCE ? 1u << 31 : 0u);
+    // the halves that carry the sequence number go last (x86 keeps the order of stores): a record the device reads is
+    // either complete or still shows the old number
+    volatile unsigned long long* ra = reinterpret_cast<volatile unsigned long long*>(&st.res_mb->a);
+    volatile unsigned long long* rb = reinterpret_cast<volatile unsigned long long*>(&st.res_mb->b);
+    ra[1] = (unsigned long long)packed_lo | (unsigned long long)packed_hi << 32;
+    rb[1] = (unsigned long long)(uint32_t)(seed >> 32);                                   // seed_hi, stop = 0
+    std::atomic_thread_fence(std::memory_order_release);
+    rb[0] = (unsigned long long)seq | (unsigned long long)(uint32_t)seed << 32;
+    ra[0] = (unsigned long long)seq | (unsigned long long)(uint32_t)trials << 32;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    if (!st.res_running) { int rc = resident_launch(ds, st); if (rc) return rc; }
+    int relaunches = 0;
+    for (long spins = 0;; spins++) {
+        if ((unsigned int)mb->done.seq == seq) break;
+        if (mb->exited == st.res_launch_id) {                 // the server has left (idle limit): was this request served?
+            std::atomic_thread_fence(std::memory_order_acquire);
+            if ((unsigned int)mb->done.seq == seq) break;
+            st.res_running = false;
+            if (++relaunches > 3) return fail(NPK_ERR_CUDA, "the resident server keeps leaving without serving the request");
+            cudaError_t e = cudaStreamSynchronize(st.stream);
+            if (e != cudaSuccess) return cuda_fail(e, "resident kernel");
+            int rc = resident_launch(ds, st);
+            if (rc) return rc;
+        }
+        if (spins > 400000000L) return fail(NPK_ERR_CUDA, "the resident server did not answer");
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    wins_strict[0] = mb->done.wins; ties[0] = mb->done.ties;
+    return NPK_OK;
+}
+
+// One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in device memory
+// between calls (the last warp hands them over and zeroes them), the result lands in mapped host memory together with the
+// call's sequence number, and the host spins on that number instead of asking the driver to synchronise the stream.
+// No H2D / D2H copy, no memset, no cudaStreamSynchronize on the fast path.
+int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, int players, int64_t trials,
+                 uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+{
+    cudaError_t e;
     if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
         return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
     if (trials < 0) return fail(NPK_ERR_INVALID_ARGUMENT, "negative size");
+    if (st.res_enabled && !win_types && !passes && trials < npk::kResidentMaxTrials)
+        return resident_query(ds, st, hole, board, players, trials, seed, deal_mode, wins_strict, ties);
+    st.stop_resident();                            // this path launches on the stream the server would be holding
+    const int known = validate_one(hole, board, players);
+    if (known < 0) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
     if (!st.single) {
         if ((e = cudaHostAlloc(&st.single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
         std::memset(st.single_host, 0, sizeof(npk::SingleResult));
@@ -667,6 +779,7 @@ int host_submit(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8
                 int64_t trials, uint64_t seed, int deal_mode, uint32_t want, int64_t* ticket)
 {
     (void)ds;
+    if (st.res_running) st.stop_resident();          // a batch needs the SMs the resident server is holding
     int free_slot = -1;
     for (int i = 0; i < kHostSlots && free_slot < 0; i++)
         if (st.slot[i].ticket < 0) free_slot = i;
@@ -821,6 +934,36 @@ int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, 
                                (want & 2u) ? out + 11 : nullptr);
     return single_query(ds, st, q, q + 2, players, trials, seed, deal_mode, out, out + 1, (want & 1u) ? out + 2 : nullptr,
                         (want & 2u) ? out + 11 : nullptr);
+}
+
+int npk_resident_start(int ctas, int idle_us)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    HostStage* st;
+    if ((rc = thread_stage(&st))) return rc;
+    if (ctas <= 0 || ctas > ds->sm_count) ctas = ds->sm_count;
+    if (ctas > 255) ctas = 255;                              // the CTA count of the packed accumulator has 8 bits
+    if (idle_us <= 0) idle_us = 200;
+    if (idle_us > 100000) idle_us = 100000;                  // the kernel must never hold the device for long on its own
+    st->stop_resident();
+    st->res_ctas = ctas;
+    st->res_idle_cycles = (long long)idle_us * ds->clock_khz / 1000;
+    st->res_enabled = true;
+    return resident_launch(ds, *st);
+}
+
+int npk_resident_stop(void)
+{
+    DeviceState* ds;
+    int rc = current_state(&ds);
+    if (rc) return rc;
+    HostStage* st;
+    if ((rc = thread_stage(&st))) return rc;
+    st->res_enabled = false;
+    st->stop_resident();
+    return NPK_OK;
 }
 
 // ---- trial-sharded jobs: count reduction over NVLink peer memory inside the kernel -----------------------------------------

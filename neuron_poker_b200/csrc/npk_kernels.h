@@ -33,6 +33,31 @@ struct SingleCall {               // in device memory
     SingleResult* host;
 };
 
+// Resident mode of the one-query path (opt-in, npk_resident_start): a persistent kernel keeps the tables staged on its SMs and
+// serves get_equity calls out of a mailbox in mapped host memory -- no kernel launch per call.  Thread 0 of CTA 0 polls the
+// mailbox over PCIe (two 16-byte reads in flight per poll) and re-publishes a new request as two 16-byte records in device
+// memory, stamped with a command number; thread 0 of every other CTA spins on those records in L2.  The warps take the
+// request's work items by static striding (spread over the CTAs first), add their counts into shared memory, and every CTA
+// hands {wins, ties, 1} to ONE packed 64-bit atomic: the CTA whose addition completes the count knows the totals from the
+// value the atomic returned and stores wins, ties and the call's sequence number to the host in one 16-byte store.
+// The kernel leaves on its own once no request has arrived for `idle_cycles` (or the host raises `stop`).
+struct __align__(128) ResidentMailbox {       // mapped host memory
+    // host -> device: two 16-byte records, both stamped with the call's sequence number (a request is taken when both match)
+    struct __align__(16) ReqA { unsigned int seq, trials, packed_lo, packed_hi; } a;   // packed_hi: board bytes 2..4, players << 24, reference dealer << 31
+    struct __align__(16) ReqB { unsigned int seq, seed_lo, seed_hi, stop; } b;         // stop: launch id the host wants to leave
+    unsigned long long pad0_[12];
+    // device -> host
+    struct __align__(16) Done { unsigned int wins, ties; unsigned long long seq; } done;
+    unsigned long long exited;                // launch id of the last server that left (written after its final poll)
+    unsigned long long pad1_[13];
+};
+struct __align__(128) ResidentState {         // device memory
+    uint4 a;                                  // {command number, trials, packed_lo, packed_hi}
+    uint4 b;                                  // {command number, seed_lo, seed_hi, host sequence number (0 = leave)}
+    unsigned long long acc[2];                // per command parity: wins | ties << 28 | CTAs done << 56
+};
+constexpr long long kResidentMaxTrials = 1ll << 28;      // counters are packed 28 + 28 + 8 bits
+
 // Trial-sharded jobs (one query spans several GPUs): the count reduction is part of the Monte-Carlo kernel.
 // Every rank owns one PeerBuf in its own HBM, mapped into every other rank's address space (CUDA IPC over NVLink):
 //   flags[parity][r]          epoch of the last block rank r has pushed into slots[parity][r] of THIS buffer
@@ -108,6 +133,8 @@ size_t aux_smem(const DeviceTables& t);
 cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long long items, int sm_count, int forced_warps,
                                   cudaStream_t s);
 cudaError_t launch_equity_mixed(const EquityParams& p, int sm_count, cudaStream_t s);
+cudaError_t launch_equity_resident(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, unsigned long long launch_id,
+                                   unsigned int last_seq, long long idle_cycles, int ctas, cudaStream_t s);
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_equity_ranges_fast(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);

@@ -85,6 +85,139 @@ __global__ void __launch_bounds__(kMixedThreads, 1) equity_mixed_kernel(const Eq
     }
 }
 
+// =====================================================================================================================
+// Resident one-query server (npk_resident_start; protocol in npk_kernels.h).  Same per-shape bodies as the mixed kernel, the
+// tables staged ONCE for the lifetime of the kernel; per request: poll (PCIe) -> gen (L2) -> items by static striding ->
+// one ticket per CTA -> 16-byte result store to the host.  What get_equity (tools/montecarlo_python.py:401-406) costs
+// per call is then the work itself plus two PCIe crossings, not a kernel launch.
+// =====================================================================================================================
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v4(void* p, uint4 v)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int REF>
+__device__ __forceinline__ void dispatch_players(int players, int known, const EquityParams* p, const WarpCtx* cx, long long b,
+                                                 long long e)
+{
+    switch (players - 1) {
+        case 0: dispatch_known<0, REF>(known, p, cx, 0, b, e); break;
+        case 1: dispatch_known<1, REF>(known, p, cx, 0, b, e); break;
+        case 2: dispatch_known<2, REF>(known, p, cx, 0, b, e); break;
+        case 3: dispatch_known<3, REF>(known, p, cx, 0, b, e); break;
+        case 4: dispatch_known<4, REF>(known, p, cx, 0, b, e); break;
+        case 5: dispatch_known<5, REF>(known, p, cx, 0, b, e); break;
+        case 6: dispatch_known<6, REF>(known, p, cx, 0, b, e); break;
+        case 7: dispatch_known<7, REF>(known, p, cx, 0, b, e); break;
+        case 8: dispatch_known<8, REF>(known, p, cx, 0, b, e); break;
+        default: dispatch_known<9, REF>(known, p, cx, 0, b, e); break;
+    }
+}
+
+__global__ void __launch_bounds__(kMixedThreads, 1)
+equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMailbox* mb, const unsigned long long launch_id,
+                       const unsigned int last_seq, const long long idle_cycles)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint4 s_a, s_b;                               // the current command
+    __shared__ unsigned long long s_cnt[2];                  // this CTA's wins, ties of the current request
+    EquityParams p{};
+    p.tables = tables;
+    const WarpCtx cx = warp_context(p, smem, 64 + 50 * 32);
+    const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned int total_warps = gridDim.x * warps;
+    unsigned int cmd = 0;                                    // commands seen so far (the state block is zeroed before the launch)
+    unsigned int seq_seen = last_seq;
+    long long t_last = clock64();
+    for (;;) {
+        if (threadIdx.x == 0) {
+            uint4 a, b;
+            if (blockIdx.x == 0) {
+                // the poller: wait for a request with a new sequence number in both records, a stop request, or the idle limit
+                bool leave = false;
+                for (;;) {
+                    a = ld_volatile_v4(&mb->a);
+                    b = ld_volatile_v4(&mb->b);
+                    if (a.x == b.x && a.x != seq_seen) break;
+                    if (b.w == (unsigned int)launch_id || clock64() - t_last > idle_cycles) { leave = true; break; }
+                }
+                seq_seen = leave ? seq_seen : a.x;
+                a.x = cmd + 1; b.w = leave ? 0u : b.x; b.x = cmd + 1;
+                st_volatile_v4(&st->a, a);
+                st_volatile_v4(&st->b, b);
+                st->acc[(cmd + 2) & 1] = 0;                  // the accumulator of the command after this one (idle since cmd - 1)
+                __threadfence();
+            } else {
+                do {
+                    a = ld_volatile_v4(&st->a);
+                    b = ld_volatile_v4(&st->b);
+                } while (a.x != cmd + 1 || b.x != cmd + 1);
+            }
+            s_a = a; s_b = b;
+            s_cnt[0] = 0; s_cnt[1] = 0;
+        }
+        __syncthreads();
+        cmd++;
+        const uint4 a = s_a, b = s_b;
+        if (b.w == 0u) break;                                // leave
+        const unsigned int trials = a.y, hi = a.w;
+        unsigned int chunk = trials / (8u * total_warps);
+        chunk = (chunk + 63u) / 64u * 64u;
+        chunk = chunk < 64u ? 64u : (chunk > 2048u ? 2048u : chunk);
+        const unsigned int chunks = (trials + chunk - 1u) / chunk;
+        const int players = (int)(hi >> 24 & 15u);
+        const unsigned long long packed = (unsigned long long)a.z | (unsigned long long)(hi & 0xFFFFFFu) << 32;
+        int known = 0;
+#pragma unroll
+        for (int i = 0; i < 5; i++) known += (packed >> (16 + 8 * i) & 0xFFull) != 0xFFull;
+        p.hole = nullptr; p.inline_query = packed;
+        p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
+        p.seed_lo = b.y; p.seed_hi = b.z;
+        p.chunk = chunk; p.chunks = chunks;
+        p.wins = &s_cnt[0]; p.ties = &s_cnt[1];              // generic pointers to shared memory: one RED.shared per warp and item
+        // items spread over the CTAs first: a 10,000-trial call (157 items of 64 trials) puts one or two warps on every SM
+        for (unsigned int item = warp * gridDim.x + blockIdx.x; item < chunks; item += total_warps) {
+            const long long t_begin = (long long)item * chunk;
+            const long long t_end = min((long long)trials, t_begin + (long long)chunk);
+            if (hi >> 31) dispatch_players<1>(players, known, &p, &cx, t_begin, t_end);
+            else dispatch_players<0>(players, known, &p, &cx, t_begin, t_end);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long mine = s_cnt[0] | s_cnt[1] << 28 | 1ull << 56;
+            const unsigned long long old = atomicAdd(&st->acc[cmd & 1], mine);
+            if ((old >> 56) == gridDim.x - 1u) {             // this CTA completes the count: old + mine are the totals
+                const unsigned long long tot = old + mine;
+                asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&mb->done), "r"((unsigned int)(tot & 0xFFFFFFFu)),
+                             "r"((unsigned int)(tot >> 28 & 0xFFFFFFFu)), "r"(b.w), "r"(0u)
+                             : "memory");
+            }
+            t_last = clock64();
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(&mb->exited) = launch_id;
+    }
+}
+
+cudaError_t launch_equity_resident(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, unsigned long long launch_id,
+                                   unsigned int last_seq, long long idle_cycles, int ctas, cudaStream_t s)
+{
+    const size_t fixed = 128 + (size_t)t.value_bytes + t.rowoff_bytes + t.flush_bytes + kDescBytes;
+    const size_t smem = fixed + (size_t)(kMixedThreads / 32) * (64 + 50 * 32) * 4;
+    cudaError_t e = cudaFuncSetAttribute(equity_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    equity_resident_kernel<<<ctas, kMixedThreads, smem, s>>>(t, st, mb, launch_id, last_seq, idle_cycles);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_equity_mixed(const EquityParams& p, int sm_count, cudaStream_t s)
 {
     auto k = p.reference_dealer ? equity_mixed_kernel<1> : equity_mixed_kernel<0>;

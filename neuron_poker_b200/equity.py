@@ -182,6 +182,16 @@ def equity_counts_batch(hole, board, n_players, trials, seed_value=0, deal_mode=
     return out
 
 
+def resident(on=True, sms=0, idle_us=200):
+    """Resident mode of the one-query calls of THIS thread (get_equity, montecarlo, equity_counts without win types / passes):
+    npk_resident_start keeps a persistent kernel with the tables staged on `sms` SMs (0 = all) that takes every call from a
+    mailbox in mapped host memory instead of being launched per call; it leaves by itself after `idle_us` microseconds without
+    a call and is restarted by the next one.  Same results bit for bit; while it is resident other GPU work waits for its SMs,
+    hence opt-in (tight get_equity loops: single-environment stepping).  resident(False) returns to one launch per call."""
+    L = _lib.ensure_current(_device())
+    _lib.check(L.npk_resident_start(int(sms), int(idle_us)) if on else L.npk_resident_stop())
+
+
 def get_equity(player_cards, table_cards, players, runs):
     """Get equity from a montecarlo run -- drop-in for tools/montecarlo_python.py:401-406 (reference dealing)."""
     r = equity_counts(player_cards, table_cards, players, runs, "reference")

@@ -613,3 +613,51 @@ def test_pipelined_host_batches_equal_blocking_calls(torch_mod):
         assert (r["wins"] == first["wins"]).all()
     L = npk._lib.lib()
     assert L.npk_equity_host_wait(10**6, None, None, None, None) < 0
+
+
+def test_resident_server_equals_launch_per_call(torch_mod):
+    """Resident mode (npk_resident_start): a persistent kernel serves the one-query calls of this thread from a mailbox in
+    mapped host memory.  Same counters as the launch-per-call path for every shape and both dealers; the server leaves after its
+    idle limit and the next call starts it again; calls it does not serve (win types, batches) stop it first; errors as before."""
+    import time
+    spots = [({"AS", "KS"}, {"2C", "7D", "KH"}, 6), ({"3H", "3S"}, {"8S", "4S", "QH", "8C", "4H"}, 2), ({"TD", "7D"}, set(), 4),
+             ({"QC", "QD"}, {"2C", "7D", "KH", "9S"}, 3), ({"2C", "2D"}, set(), 10), ({"AH", "KD"}, {"2C", "7D", "KH"}, 1)]
+    runs = [10000, 777, 64, 1, 130000, 0]
+    want = {}
+    for i, (h, b, n) in enumerate(spots):
+        for mode in ("uniform", "reference"):
+            for t in runs:
+                r = npk.equity_counts(h, b, n, t, deal_mode=mode, seed_value=100 + i)
+                want[(i, mode, t)] = (r["wins"], r["ties"])
+    try:
+        npk.resident(True, idle_us=300)
+        for rep in range(3):
+            for i, (h, b, n) in enumerate(spots):
+                for mode in ("uniform", "reference"):
+                    for t in runs:
+                        r = npk.equity_counts(h, b, n, t, deal_mode=mode, seed_value=100 + i)
+                        assert (r["wins"], r["ties"]) == want[(i, mode, t)], (rep, i, mode, t)
+            time.sleep(0.02)                               # the server has left by now: the next call restarts it
+        eq = npk.get_equity({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 10000)
+        assert 0.3 < eq < 0.9
+        h, b, n = spots[0]
+        a = npk.equity_counts(h, b, n, 5000, deal_mode="reference", seed_value=5, win_types=True, passes=True)   # launch path
+        npk.resident(False)
+        c = npk.equity_counts(h, b, n, 5000, deal_mode="reference", seed_value=5, win_types=True, passes=True)
+        assert a == c
+        npk.resident(True, sms=16, idle_us=100000)         # a server on 16 SMs that stays
+        r = npk.equity_counts(h, b, n, 10000, deal_mode="uniform", seed_value=100)
+        assert (r["wins"], r["ties"]) == want[(0, "uniform", 10000)]
+        hole = np.array([[50, 51]] * 40, dtype=np.uint8)
+        board = np.full((40, 5), NO, dtype=np.uint8)
+        npl = np.full(40, 3, dtype=np.uint8)
+        b1 = npk.equity_counts_batch(hole, board, npl, 640, seed_value=9)            # stops the server, runs, returns
+        r = npk.equity_counts(h, b, n, 10000, deal_mode="uniform", seed_value=100)   # and the server comes back
+        assert (r["wins"], r["ties"]) == want[(0, "uniform", 10000)]
+        with pytest.raises(ValueError):
+            npk.get_equity({"AS", "AS"}, set(), 2, 100)
+        npk.resident(False)
+        b2 = npk.equity_counts_batch(hole, board, npl, 640, seed_value=9)
+        assert (b1["wins"] == b2["wins"]).all() and (b1["ties"] == b2["ties"]).all()
+    finally:
+        npk.resident(False)
