@@ -17,6 +17,8 @@ if [ -f $CK ]; then
 fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/${TAG}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
+timeout 300 python tools/latency.py > $O/${TAG}_latency.txt 2>&1; echo "latency rc=$?"
+timeout 300 python tools/latency_breakdown.py > $O/${TAG}_latency_breakdown.txt 2>&1
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches_cfg5.csv \
     python bench.py --workload cfg5 --deal uniform --steps 3 --warmup 3 > $O/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
