@@ -58,8 +58,27 @@ def build(force=False, verbose=False, defines=(), out=None):
     return target
 
 
+FAST = os.path.join(HERE, "_npkfast.so")
+FAST_SRC = os.path.join(CSRC, "npk_pyfast.c")
+
+
+def build_fast(force=False):
+    """Compile the CPython binding of npk_equity_one (csrc/npk_pyfast.c) in-tree with gcc.  Returns its path."""
+    import sysconfig
+    if not force and os.path.exists(FAST) and os.path.getmtime(FAST) >= os.path.getmtime(FAST_SRC):
+        return FAST
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        raise RuntimeError("no C compiler for neuron_poker_b200/_npkfast.so")
+    subprocess.check_call([cc, "-O2", "-Wall", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"],
+                           "-I" + os.path.join(HERE, "..", "include"), FAST_SRC, "-o", FAST])
+    return FAST
+
+
 if __name__ == "__main__":
     import sys
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
     outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))
+    if not outs:
+        print(build_fast(force="--force" in sys.argv))

@@ -75,6 +75,27 @@ def lib():
     return _lib
 
 
+_fast = None
+
+
+def fast():
+    """The CPython binding of npk_equity_one (csrc/npk_pyfast.c), bound to the loaded libnpk.so; built on first use like the
+    library itself.  A faster way into the same entry point, not another implementation."""
+    global _fast
+    if _fast is None:
+        L = lib()
+        with _lock:
+            if _fast is None:
+                import importlib.util
+                path = _build.build_fast()
+                spec = importlib.util.spec_from_file_location("_npkfast", path)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                mod.bind(ctypes.cast(L.npk_equity_one, ctypes.c_void_p).value)
+                _fast = mod
+    return _fast
+
+
 def check(rc):
     if rc < 0:
         raise NpkError(rc, lib().npk_last_error().decode())

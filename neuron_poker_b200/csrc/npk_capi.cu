@@ -80,6 +80,8 @@ struct HostStage {
     npk::ResidentState* res_state = nullptr;      // device memory
     unsigned long long res_launch_id = 0;
     unsigned int res_seq = 0;
+    unsigned int oneshot_parity = 0;              // accumulator the next launched one-query call uses
+    bool res_dirty = false;                       // a server has used the state block since the last launched call
     void stop_resident();
     void release()
     {
@@ -125,11 +127,13 @@ struct Tuning {
     long long chunk = 0;        // NPK_CHUNK: trials per work item
     int warps = 0;              // NPK_WARPS: warps per CTA of the Monte-Carlo kernels
     bool no_single_path = false;// NPK_NO_SINGLE_PATH: one-query host calls through the general path
+    bool no_oneshot = false;    // NPK_NO_ONESHOT: launched one-query calls through the shape's own kernel (per-warp hand-over)
     Tuning()
     {
         if (const char* e = getenv("NPK_CHUNK")) chunk = atoll(e);
         if (const char* e = getenv("NPK_WARPS")) warps = atoi(e);
         no_single_path = getenv("NPK_NO_SINGLE_PATH") != nullptr;
+        no_oneshot = getenv("NPK_NO_ONESHOT") != nullptr;
     }
 };
 const Tuning& tuning()
@@ -613,15 +617,24 @@ int validate_one(const uint8_t* hole, const uint8_t* board, int players)
 
 // (Re)start this thread's resident server on its stream.  `completed` = sequence number of the last request whose result has
 // been received: a request posted after it is picked up by the new server at its first poll.
+int resident_buffers(HostStage& st)
+{
+    cudaError_t e;
+    if (st.res_mb) return NPK_OK;
+    if ((e = cudaHostAlloc(&st.res_mb, sizeof(npk::ResidentMailbox), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
+    std::memset(st.res_mb, 0, sizeof(npk::ResidentMailbox));
+    if ((e = cudaHostGetDevicePointer(&st.res_mb_dev, st.res_mb, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
+    if ((e = cudaMalloc(&st.res_state, sizeof(npk::ResidentState))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMemset(st.res_state, 0, sizeof(npk::ResidentState))) != cudaSuccess) return cuda_fail(e, "cudaMemset");
+    return NPK_OK;
+}
+
 int resident_launch(DeviceState* ds, HostStage& st)
 {
     cudaError_t e;
-    if (!st.res_mb) {
-        if ((e = cudaHostAlloc(&st.res_mb, sizeof(npk::ResidentMailbox), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
-        std::memset(st.res_mb, 0, sizeof(npk::ResidentMailbox));
-        if ((e = cudaHostGetDevicePointer(&st.res_mb_dev, st.res_mb, 0)) != cudaSuccess) return cuda_fail(e, "cudaHostGetDevicePointer");
-        if ((e = cudaMalloc(&st.res_state, sizeof(npk::ResidentState))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    }
+    int rc = resident_buffers(st);
+    if (rc) return rc;
+    st.res_dirty = true;
     if ((e = cudaMemsetAsync(st.res_state, 0, sizeof(npk::ResidentState), st.stream)) != cudaSuccess) return cuda_fail(e, "memset");
     const unsigned int completed = (unsigned int)const_cast<volatile npk::ResidentMailbox*>(st.res_mb)->done.seq;
     ++st.res_launch_id;
@@ -699,6 +712,44 @@ int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint
     st.stop_resident();                            // this path launches on the stream the server would be holding
     const int known = validate_one(hole, board, players);
     if (known < 0) return fail(NPK_ERR_INVALID_CARDS, "query 0: card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+    if (!win_types && !passes && trials < npk::kResidentMaxTrials && !tuning().no_oneshot) {
+        // the common call: a kernel launched for this request, handing over like the resident server (npk_mixed.cu)
+        wins_strict[0] = 0; ties[0] = 0;
+        if (trials == 0) return NPK_OK;
+        int rc = resident_buffers(st);
+        if (rc) return rc;
+        if (st.res_dirty) {
+            if ((e = cudaMemsetAsync(st.res_state, 0, sizeof(npk::ResidentState), st.stream)) != cudaSuccess) return cuda_fail(e, "memset");
+            st.oneshot_parity = 0;
+            st.res_dirty = false;
+        }
+        unsigned int seq = ++st.res_seq;
+        if (seq == 0) seq = ++st.res_seq;
+        const uint4 a = make_uint4(0u, (unsigned int)trials,
+                                   (unsigned int)hole[0] | (unsigned int)hole[1] << 8 | (unsigned int)board[0] << 16 |
+                                       (unsigned int)board[1] << 24,
+                                   (unsigned int)board[2] | (unsigned int)board[3] << 8 | (unsigned int)board[4] << 16 |
+                                       (unsigned int)players << 24 | (deal_mode == NPK_DEAL_REFERENCE ? 1u << 31 : 0u));
+        const uint4 b = make_uint4(0u, (unsigned int)seed, (unsigned int)(seed >> 32), seq);
+        e = npk::launch_equity_oneshot(ds->t, st.res_state, st.res_mb_dev, a, b, st.oneshot_parity, ds->sm_count, st.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "equity kernel launch");
+        st.oneshot_parity ^= 1u;
+        volatile npk::ResidentMailbox* mb = st.res_mb;
+        bool arrived = false;
+        for (long spins = 0; spins < 4000000; spins++) {          // a few hundred ms at most, then ask the driver
+            if ((unsigned int)mb->done.seq == seq) { arrived = true; break; }
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (!arrived) {
+            if ((e = cudaStreamSynchronize(st.stream)) != cudaSuccess) return cuda_fail(e, "equity kernel");
+            if ((unsigned int)mb->done.seq != seq) return fail(NPK_ERR_CUDA, "the one-query kernel finished without publishing its result");
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        wins_strict[0] = mb->done.wins; ties[0] = mb->done.ties;
+        return NPK_OK;
+    }
     if (!st.single) {
         if ((e = cudaHostAlloc(&st.single_host, sizeof(npk::SingleResult), cudaHostAllocMapped)) != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
         std::memset(st.single_host, 0, sizeof(npk::SingleResult));

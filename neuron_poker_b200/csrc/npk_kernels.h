@@ -135,6 +135,8 @@ cudaError_t launch_equity_uniform(int nopp, int nb, const EquityParams& p, long 
 cudaError_t launch_equity_mixed(const EquityParams& p, int sm_count, cudaStream_t s);
 cudaError_t launch_equity_resident(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, unsigned long long launch_id,
                                    unsigned int last_seq, long long idle_cycles, int ctas, cudaStream_t s);
+cudaError_t launch_equity_oneshot(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, uint4 a, uint4 b,
+                                  unsigned int parity, int sm_count, cudaStream_t s);
 cudaError_t launch_equity_ranges(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_equity_ranges_fast(int deal_mode, const EquityParams& p, int grid, cudaStream_t s);
 cudaError_t launch_rank7(const DeviceTables& t, const uint8_t* cards, long long n, uint16_t* out, int grid, cudaStream_t s);

@@ -120,6 +120,48 @@ __device__ __forceinline__ void dispatch_players(int players, int known, const E
     }
 }
 
+// One request on the warps of this grid: a = {-, trials, packed_lo, packed_hi}, b = {-, seed_lo, seed_hi, sequence number}.
+// The CTA's counts go to s_cnt (shared), then ONE packed atomic per CTA on *acc; the CTA that completes the count publishes.
+__device__ __forceinline__ void serve_request(EquityParams& p, const WarpCtx& cx, const uint4 a, const uint4 b,
+                                              unsigned long long* s_cnt, unsigned long long* acc, ResidentMailbox* mb)
+{
+    const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const unsigned int total_warps = gridDim.x * warps;
+    const unsigned int trials = a.y, hi = a.w;
+    unsigned int chunk = trials / (8u * total_warps);
+    chunk = (chunk + 63u) / 64u * 64u;
+    chunk = chunk < 64u ? 64u : (chunk > 2048u ? 2048u : chunk);
+    const unsigned int chunks = (trials + chunk - 1u) / chunk;
+    const int players = (int)(hi >> 24 & 15u);
+    const unsigned long long packed = (unsigned long long)a.z | (unsigned long long)(hi & 0xFFFFFFu) << 32;
+    int known = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) known += (packed >> (16 + 8 * i) & 0xFFull) != 0xFFull;
+    p.hole = nullptr; p.inline_query = packed;
+    p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
+    p.seed_lo = b.y; p.seed_hi = b.z;
+    p.chunk = chunk; p.chunks = chunks;
+    p.wins = &s_cnt[0]; p.ties = &s_cnt[1];              // generic pointers to shared memory: one RED.shared per warp and item
+    // items spread over the CTAs first: a 10,000-trial call (157 items of 64 trials) puts one or two warps on every SM
+    for (unsigned int item = warp * gridDim.x + blockIdx.x; item < chunks; item += total_warps) {
+        const long long t_begin = (long long)item * chunk;
+        const long long t_end = min((long long)trials, t_begin + (long long)chunk);
+        if (hi >> 31) dispatch_players<1>(players, known, &p, &cx, t_begin, t_end);
+        else dispatch_players<0>(players, known, &p, &cx, t_begin, t_end);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long mine = s_cnt[0] | s_cnt[1] << 28 | 1ull << 56;
+        const unsigned long long old = atomicAdd(acc, mine);
+        if ((old >> 56) == gridDim.x - 1u) {             // this CTA completes the count: old + mine are the totals
+            const unsigned long long tot = old + mine;
+            asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&mb->done), "r"((unsigned int)(tot & 0xFFFFFFFu)),
+                         "r"((unsigned int)(tot >> 28 & 0xFFFFFFFu)), "r"(b.w), "r"(0u)
+                         : "memory");
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMixedThreads, 1)
 equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMailbox* mb, const unsigned long long launch_id,
                        const unsigned int last_seq, const long long idle_cycles)
@@ -130,8 +172,6 @@ equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMai
     EquityParams p{};
     p.tables = tables;
     const WarpCtx cx = warp_context(p, smem, 64 + 50 * 32);
-    const int warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const unsigned int total_warps = gridDim.x * warps;
     unsigned int cmd = 0;                                    // commands seen so far (the state block is zeroed before the launch)
     unsigned int seq_seen = last_seq;
     long long t_last = clock64();
@@ -166,45 +206,33 @@ equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMai
         cmd++;
         const uint4 a = s_a, b = s_b;
         if (b.w == 0u) break;                                // leave
-        const unsigned int trials = a.y, hi = a.w;
-        unsigned int chunk = trials / (8u * total_warps);
-        chunk = (chunk + 63u) / 64u * 64u;
-        chunk = chunk < 64u ? 64u : (chunk > 2048u ? 2048u : chunk);
-        const unsigned int chunks = (trials + chunk - 1u) / chunk;
-        const int players = (int)(hi >> 24 & 15u);
-        const unsigned long long packed = (unsigned long long)a.z | (unsigned long long)(hi & 0xFFFFFFu) << 32;
-        int known = 0;
-#pragma unroll
-        for (int i = 0; i < 5; i++) known += (packed >> (16 + 8 * i) & 0xFFull) != 0xFFull;
-        p.hole = nullptr; p.inline_query = packed;
-        p.trials = trials; p.trial_offset = 0; p.query_offset = 0;
-        p.seed_lo = b.y; p.seed_hi = b.z;
-        p.chunk = chunk; p.chunks = chunks;
-        p.wins = &s_cnt[0]; p.ties = &s_cnt[1];              // generic pointers to shared memory: one RED.shared per warp and item
-        // items spread over the CTAs first: a 10,000-trial call (157 items of 64 trials) puts one or two warps on every SM
-        for (unsigned int item = warp * gridDim.x + blockIdx.x; item < chunks; item += total_warps) {
-            const long long t_begin = (long long)item * chunk;
-            const long long t_end = min((long long)trials, t_begin + (long long)chunk);
-            if (hi >> 31) dispatch_players<1>(players, known, &p, &cx, t_begin, t_end);
-            else dispatch_players<0>(players, known, &p, &cx, t_begin, t_end);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long mine = s_cnt[0] | s_cnt[1] << 28 | 1ull << 56;
-            const unsigned long long old = atomicAdd(&st->acc[cmd & 1], mine);
-            if ((old >> 56) == gridDim.x - 1u) {             // this CTA completes the count: old + mine are the totals
-                const unsigned long long tot = old + mine;
-                asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(&mb->done), "r"((unsigned int)(tot & 0xFFFFFFFu)),
-                             "r"((unsigned int)(tot >> 28 & 0xFFFFFFFu)), "r"(b.w), "r"(0u)
-                             : "memory");
-            }
-            t_last = clock64();
-        }
+        serve_request(p, cx, a, b, s_cnt, &st->acc[cmd & 1], mb);
+        if (threadIdx.x == 0) t_last = clock64();
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
         *reinterpret_cast<volatile unsigned long long*>(&mb->exited) = launch_id;
     }
+}
+
+// The same request served by a kernel launched for it (the default one-query path, npk_equity_one without resident mode):
+// the request travels in the kernel parameters, a few small CTAs (four warps each while the call has few items) stage the tables,
+// and the hand-over is the packed atomic + 16-byte store of the resident server instead of per-warp counters, a ticket and a
+// read-back.  `parity` alternates between calls; the other accumulator is cleared for the next call.
+__global__ void __launch_bounds__(kMixedThreads, 1)
+equity_oneshot_kernel(const DeviceTables tables, ResidentState* st, ResidentMailbox* mb, const uint4 a, const uint4 b,
+                      const unsigned int parity)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ unsigned long long s_cnt[2];
+    EquityParams p{};
+    p.tables = tables;
+    if (threadIdx.x == 0) {
+        s_cnt[0] = 0; s_cnt[1] = 0;
+        if (blockIdx.x == 0) st->acc[parity ^ 1u] = 0;
+    }
+    const WarpCtx cx = warp_context(p, smem, 64 + 50 * 32);       // (synchronises the CTA while it stages the tables)
+    serve_request(p, cx, a, b, s_cnt, &st->acc[parity], mb);
 }
 
 cudaError_t launch_equity_resident(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, unsigned long long launch_id,
@@ -215,6 +243,30 @@ cudaError_t launch_equity_resident(const DeviceTables& t, ResidentState* st, Res
     cudaError_t e = cudaFuncSetAttribute(equity_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     equity_resident_kernel<<<ctas, kMixedThreads, smem, s>>>(t, st, mb, launch_id, last_seq, idle_cycles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_equity_oneshot(const DeviceTables& t, ResidentState* st, ResidentMailbox* mb, uint4 a, uint4 b,
+                                  unsigned int parity, int sm_count, cudaStream_t s)
+{
+    const long long items = ((long long)a.y + 63) / 64;
+    const int warps = items <= 4ll * sm_count ? 4 : kMixedThreads / 32;
+    long long grid = (items + warps - 1) / warps;
+    if (grid < 1) grid = 1;
+    if (grid > sm_count) grid = sm_count;
+    if (grid > 255) grid = 255;                              // the CTA count of the packed accumulator has 8 bits
+    const size_t fixed = 128 + (size_t)t.value_bytes + t.rowoff_bytes + t.flush_bytes + kDescBytes;
+    const size_t smem_max = fixed + (size_t)(kMixedThreads / 32) * (64 + 50 * 32) * 4;
+    const size_t smem = fixed + (size_t)warps * (64 + 50 * 32) * 4;
+    static bool opted[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !opted[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(equity_oneshot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) opted[dev] = true;
+    }
+    equity_oneshot_kernel<<<(int)grid, warps * 32, smem, s>>>(t, st, mb, a, b, parity);
     return cudaGetLastError();
 }
 

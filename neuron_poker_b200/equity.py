@@ -192,8 +192,27 @@ def resident(on=True, sms=0, idle_us=200):
     _lib.check(L.npk_resident_start(int(sms), int(idle_us)) if on else L.npk_resident_stop())
 
 
+_fast_equity = None
+
+
+def _fast_call(player_cards, table_cards, players, runs, mode):
+    """The common case of a one-query call through the C binding (csrc/npk_pyfast.c): card strings -> npk_equity_one -> float
+    without Python byte code in between.  None = not the common case, or an error: the caller runs the Python implementation,
+    which raises the reference's exceptions."""
+    global _fast_equity
+    f = _fast_equity
+    if f is None:
+        f = _fast_equity = _lib.fast().equity
+    _lib.ensure_current(_device())
+    rng = _seed_state["rng"]            # the call's Philox seed comes from the generator _next_seed uses
+    return f(player_cards, table_cards, players, runs, mode, _global_sample if rng is None else rng.random_sample)
+
+
 def get_equity(player_cards, table_cards, players, runs):
     """Get equity from a montecarlo run -- drop-in for tools/montecarlo_python.py:401-406 (reference dealing)."""
+    e = _fast_call(player_cards, table_cards, players, runs, DEAL_REFERENCE)
+    if e is not None:
+        return e
     r = equity_counts(player_cards, table_cards, players, runs, "reference")
     return (r["wins"] + r["ties"]) / runs
 
@@ -204,6 +223,9 @@ def montecarlo(my_cards, cards_on_table, number_of_players, iterations):
     table = list(cards_on_table)
     if len(table) < 3:
         table = []
+    e = _fast_call(my_cards, table, number_of_players, iterations, DEAL_UNIFORM)
+    if e is not None:
+        return e
     try:
         r = equity_counts(my_cards, table, number_of_players, iterations, deal_mode="uniform")
     except ValueError as exc:                   # pybind11 surfaces std::runtime_error as RuntimeError

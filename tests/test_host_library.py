@@ -207,3 +207,49 @@ def test_reference_dealer_without_retries_is_the_reference_distribution():
         raw = [rnd.randrange(n - k) for k in range(d)]
         lst = list(range(n))
         assert [lst.pop(i) for i in raw] == sm.lehmer_slots(raw)
+
+
+def test_c_binding_of_the_one_query_call_packs_like_the_python_path():
+    """neuron_poker_b200/_npkfast.so (csrc/npk_pyfast.c) is a second way into npk_equity_one: against a recording stand-in for
+    that entry point (no GPU needed) it passes the same packed query, player count, trial count, dealing mode and seed as
+    equity.equity_counts would, and hands everything that is not the common case back to Python (None)."""
+    import ctypes
+    import importlib.util
+    from neuron_poker_b200 import _build, _lib
+    from neuron_poker_b200.equity import _pack_query
+    path = _build.build_fast()
+    spec = importlib.util.spec_from_file_location("_npkfast", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.bind(0)
+    assert mod.equity({"AS", "KS"}, set(), 2, 100, 1, lambda: 0.5) is None            # not bound
+    seen = []
+    proto = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
+                             ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64))
+
+    def fake(packed, players, trials, seed, mode, want, out):
+        seen.append((packed, players, trials, seed, mode, want))
+        out[0], out[1] = trials // 4, trials // 2
+        return 0 if players != 7 else -5
+
+    cb = proto(fake)
+    try:
+        mod.bind(ctypes.cast(cb, ctypes.c_void_p).value)
+        _check_c_binding(mod, seen, _pack_query)
+    finally:          # the shared object has one binding per process: give it back to the real library if that is loaded
+        mod.bind(ctypes.cast(_lib._lib.npk_equity_one, ctypes.c_void_p).value if _lib._lib is not None else 0)
+
+
+def _check_c_binding(mod, seen, _pack_query):
+    cases = [({"AS", "KS"}, {"2C", "7D", "KH"}, 6), (["3H", "3S"], ("8S", "4S", "QH", "8C", "4H"), 2), (("TD", "7D"), [], 10),
+             ({"QC", "QD"}, ["2C", "7D", "KH", "9S"], np.int64(3))]
+    for hole, board, players in cases:
+        seen.clear()
+        e = mod.equity(hole, board, players, 1000, 1, lambda: 0.25)
+        assert e == 0.75
+        assert seen == [(_pack_query(hole, board), int(players), 1000, 2 ** 51, 1, 0)]
+    for bad in [({"AS"}, set(), 2, 100), ({"AS", "KS", "QS"}, set(), 2, 100), ({"AS", "Kx"}, set(), 2, 100),
+                ({"AS", "KS"}, {"null"}, 2, 100), ({"AS", "KS"}, set(), 0, 100), ({"AS", "KS"}, set(), 11, 100),
+                ({"AS", "KS"}, set(), 2, 0), ({"AS", "KS"}, set(), 2.5, 100), ({"AS", "KS"}, set(), 7, 100),
+                ("ASKS", set(), 2, 100), ({"AS", "KS"}, {"2C", "3C", "4C", "5C", "6C", "7C"}, 2, 100)]:
+        assert mod.equity(bad[0], bad[1], bad[2], bad[3], 0, lambda: 0.5) is None, bad
