@@ -692,6 +692,8 @@ def run_mc(args, wl, cx, deal, steps, warmup, peak=None, peak_detail=None, e2e=T
             assert (check["wins"] == r["wins"]).all() and (check["ties"] == r["ties"]).all()     # same seed as the last blocking step
             line["e2e"].update({"blocking_value": line["e2e"]["value"], "value": Q * t_cnt * P * world * e2e_steps / piped_s,
                                 "in_flight": 2,
+                                "note": "can exceed `value`: the steps of this leg run back to back (no L2 flush between them) "
+                                        "and the kernels of consecutive batches, on two streams, fill each other's tails",
                                 "api": "neuron_poker_b200.equity_counts_batch(block=False) -> npk_equity_host_submit / "
                                        "npk_equity_host_wait, two batches in flight; blocking_value = one blocking "
                                        "npk_equity_host call per step"})

@@ -843,23 +843,9 @@ int host_submit(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8
     for (int i = 0; i < 5; i++) uk += board[i] != 0xFF;
     bool uniform = true;
     for (int64_t q = 0; q < Q; q++) {
-        unsigned long long mask = 0;
-        int known = 0;
-        bool ended = false, bad = n_players[q] < 1 || n_players[q] > 10;
-        for (int i = 0; i < 2; i++) {
-            const int c = hole[2 * q + i];
-            if (c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
-            mask |= 1ull << c;
-        }
-        for (int i = 0; i < 5 && !bad; i++) {
-            const int c = board[5 * q + i];
-            if (c == 0xFF) { ended = true; continue; }
-            if (ended || c >= 52 || (mask >> c & 1ull)) { bad = true; break; }
-            mask |= 1ull << c;
-            known++;
-        }
-        if (bad) return fail(NPK_ERR_INVALID_CARDS, "query " + std::to_string(q) +
-                             ": card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
+        const int known = validate_one(hole + 2 * q, board + 5 * q, n_players[q]);
+        if (known < 0) return fail(NPK_ERR_INVALID_CARDS, "query " + std::to_string(q) +
+                                   ": card id >= 52, duplicate cards, gap in the board, or players outside 1..10");
         if (n_players[q] != up || known != uk) uniform = false;
     }
     cudaError_t e;

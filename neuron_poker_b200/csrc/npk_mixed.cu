@@ -191,8 +191,6 @@ equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMai
                 a.x = cmd + 1; b.w = leave ? 0u : b.x; b.x = cmd + 1;
                 st_volatile_v4(&st->a, a);
                 st_volatile_v4(&st->b, b);
-                st->acc[(cmd + 2) & 1] = 0;                  // the accumulator of the command after this one (idle since cmd - 1)
-                __threadfence();
             } else {
                 do {
                     a = ld_volatile_v4(&st->a);
@@ -207,7 +205,15 @@ equity_resident_kernel(const DeviceTables tables, ResidentState* st, ResidentMai
         const uint4 a = s_a, b = s_b;
         if (b.w == 0u) break;                                // leave
         serve_request(p, cx, a, b, s_cnt, &st->acc[cmd & 1], mb);
-        if (threadIdx.x == 0) t_last = clock64();
+        if (threadIdx.x == 0) {
+            if (blockIdx.x == 0) {
+                // the accumulator of the NEXT command (idle since command cmd - 1) is cleared here, off the path of the request
+                // just served and before the next one can be published (this thread is the one that publishes it)
+                st->acc[(cmd + 1) & 1] = 0;
+                __threadfence();
+            }
+            t_last = clock64();
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
