@@ -200,10 +200,11 @@ def _fast_call(player_cards, table_cards, players, runs, mode):
     without Python byte code in between.  None = not the common case, or an error: the caller runs the Python implementation,
     which raises the reference's exceptions."""
     global _fast_equity
+    if getattr(_lib._current, "device", None) != _device():
+        return None           # first call of this thread: the Python path validates the arguments, then initialises the device
     f = _fast_equity
     if f is None:
         f = _fast_equity = _lib.fast().equity
-    _lib.ensure_current(_device())
     rng = _seed_state["rng"]            # the call's Philox seed comes from the generator _next_seed uses
     return f(player_cards, table_cards, players, runs, mode, _global_sample if rng is None else rng.random_sample)
 
