@@ -77,6 +77,16 @@ for mode in ("uniform", "reference"):
         assert 0 < c["wins"] + c["ties"] <= 1000
     o = npk.equity_counts_batch(ho, bo, pl, 200, seed_value=9, deal_mode=mode, win_types=True)
     assert ((o["wins"] + o["ties"]) <= 200).all()
+    # the launched one-query call with the packed hand-over, the resident server (same counters), batches in flight
+    one = [npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, p_, 3000, deal_mode=mode, seed_value=8) for p_ in (2, 6, 10)]
+    npk.resident(True, idle_us=500)
+    res = [npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, p_, 3000, deal_mode=mode, seed_value=8) for p_ in (2, 6, 10)]
+    npk.resident(False)
+    assert one == res, (one, res)
+    pend = [npk.equity_counts_batch(ho, bo, pl, 200, seed_value=9, deal_mode=mode, win_types=True, block=False) for _ in range(3)]
+    for pnd in pend:
+        r_ = pnd.result()
+        assert (r_["wins"] == o["wins"]).all() and (r_["win_types"] == o["win_types"]).all()
     print("ok host entry points", mode, flush=True)
 
 # K1'': ranges, hero range, ghost cards
