@@ -215,6 +215,24 @@ int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint
                            uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                            uint64_t* passes);
 
+/* The same two calls with opponents whose cards are KNOWN -- the reference's "several known hands in player_card_list" (its
+ * provision for bots that share a table, tools/montecarlo_python.py:132-163): known_opp [Q, n_known, 2] (device for _batch,
+ * host for _host) holds the hands of n_known (0..9) of the n_players - 1 opponents; their cards leave the deck before anything
+ * is dealt and their hands take part in every showdown; the remaining n_players - 1 - n_known opponents are dealt from
+ * opp_allowed as before.  The hero wins a trial when his hand is strictly best among all of them (ties are counted
+ * separately, as everywhere).  Not combinable with hero_allowed: the reference draws a hero range BEFORE it removes the known
+ * hands, so that case deals duplicate cards there.  n_known = 0 is npk_equity_ranges_batch / _host. */
+int npk_equity_ranges_known_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                                  const uint8_t* known_opp, int n_known, int64_t Q, int64_t trials,
+                                  const uint64_t* opp_allowed, const uint64_t* hero_allowed, uint64_t seed,
+                                  int64_t trial_offset, int64_t query_offset, int deal_mode, uint32_t flags,
+                                  uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
+                                  void* workspace, void* stream);
+int npk_equity_ranges_known_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                                 const uint8_t* known_opp, int n_known, int64_t Q, int64_t trials, const uint64_t* opp_allowed,
+                                 const uint64_t* hero_allowed, uint64_t seed, int deal_mode, uint64_t* wins_strict,
+                                 uint64_t* ties, uint64_t* win_types, uint64_t* passes);
+
 /*
  * The evaluator entry points below take `flags`: with NPK_FLAG_VALIDATE the inputs are checked on the device first (every card
  * id < 52, no card twice in a row, n_players in range, a shape the kernel implements) and a violation is reported as

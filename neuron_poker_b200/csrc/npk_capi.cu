@@ -686,6 +686,10 @@ int resident_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const ui
             int rc = resident_launch(ds, st);
             if (rc) return rc;
         }
+        if ((spins & 0xFFFFF) == 0xFFFFF) {                   // every ~million spins: is the kernel still healthy?
+            const cudaError_t q = cudaStreamQuery(st.stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) { st.res_running = false; return cuda_fail(q, "resident kernel"); }
+        }
         if (spins > 400000000L) return fail(NPK_ERR_CUDA, "the resident server did not answer");
 #if defined(__x86_64__) || defined(__i386__)
         __builtin_ia32_pause();
@@ -1144,7 +1148,7 @@ int npk_equity_batch_sharded(void* group, const uint8_t* hole, const uint8_t* bo
 
 // ---- ranges ------------------------------------------------------------------------------------------------------------
 __global__ void validate_ranges_kernel(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players,
-                                       const uint8_t* ghost, long long Q, uint8_t* ws)
+                                       const uint8_t* ghost, const uint8_t* known_opp, int n_known, long long Q, uint8_t* ws)
 {
     uint32_t* invalid = reinterpret_cast<uint32_t*>(ws + kWsInvalid);
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += (long long)gridDim.x * blockDim.x) {
@@ -1171,8 +1175,14 @@ __global__ void validate_ranges_kernel(const uint8_t* hole, const uint8_t* board
             if ((g0 == 0xFF) != (g1 == 0xFF)) bad = 1;
             else if (g0 != 0xFF) {
                 if (g0 >= 52 || g1 >= 52 || g0 == g1) bad = 1;
-                else bad |= (int)((mask >> g0 | mask >> g1) & 1ull);
+                else { bad |= (int)((mask >> g0 | mask >> g1) & 1ull); mask |= (1ull << g0) | (1ull << g1); }
             }
+        }
+        // opponents with known cards: valid ids, no card twice anywhere, and no more of them than opponents
+        if (n_known > np - 1) bad = 1;
+        for (int f = 0; f < 2 * n_known; f++) {
+            const int c = known_opp[2 * q * n_known + f];
+            if (c >= 52) bad = 1; else { bad |= (int)(mask >> c & 1ull); mask |= 1ull << c; }
         }
         if (bad) atomicAdd(invalid, 1u);
     }
@@ -1184,6 +1194,18 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
                             uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes, void* workspace,
                             void* stream)
 {
+    return npk_equity_ranges_known_batch(hole, board, n_players, ghost, nullptr, 0, Q, trials, opp_allowed, hero_allowed, seed,
+                                         trial_offset, query_offset, deal_mode, flags, wins_strict, ties, win_types, passes,
+                                         workspace, stream);
+}
+
+int npk_equity_ranges_known_batch(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                                  const uint8_t* known_opp, int n_known, int64_t Q, int64_t trials,
+                                  const uint64_t* opp_allowed, const uint64_t* hero_allowed, uint64_t seed,
+                                  int64_t trial_offset, int64_t query_offset, int deal_mode, uint32_t flags,
+                                  uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes,
+                                  void* workspace, void* stream)
+{
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
@@ -1192,6 +1214,11 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
     if (Q > 0x7fffffffLL) return fail(NPK_ERR_INVALID_ARGUMENT, "at most 2^31-1 queries per call");
     if ((!hole && !hero_allowed) || !board || !n_players || !wins_strict || !ties || !workspace || !opp_allowed)
         return fail(NPK_ERR_INVALID_ARGUMENT, "null pointer");
+    if (n_known < 0 || n_known > 9 || (n_known > 0 && !known_opp))
+        return fail(NPK_ERR_INVALID_ARGUMENT, "n_known must be 0..9 and known_opp must be given when it is not 0");
+    if (n_known > 0 && hero_allowed)
+        return fail(NPK_ERR_INVALID_ARGUMENT, "a hero range together with known opponent hands is not supported (the reference "
+                                              "draws the hero before it removes the known hands, montecarlo_python.py:132-163)");
     if (deal_mode != NPK_DEAL_UNIFORM && deal_mode != NPK_DEAL_REFERENCE)
         return fail(NPK_ERR_INVALID_ARGUMENT, "deal_mode must be NPK_DEAL_UNIFORM or NPK_DEAL_REFERENCE");
     const uint64_t top = (1ull << (169 - 128)) - 1ull;
@@ -1207,6 +1234,7 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
     npk::EquityParams p{};
     p.tables = ds->t;
     p.hole = hero_allowed ? nullptr : hole; p.board = board; p.n_players = n_players; p.ghost = ghost;
+    p.known_opp = n_known > 0 ? known_opp : nullptr; p.n_known = (uint32_t)n_known;
     p.trials = trials; p.trial_offset = trial_offset; p.query_offset = (uint32_t)query_offset;
     p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
     const long long chunks = plan_items(p, Q, trials, ds->sm_count, 32);
@@ -1228,14 +1256,14 @@ int npk_equity_ranges_batch(const uint8_t* hole, const uint8_t* board, const uin
     const bool validate = (flags & NPK_FLAG_VALIDATE) != 0;
     if (validate) {
         const int cg = (int)std::min<long long>((Q + 255) / 256, 4 * ds->sm_count);
-        validate_ranges_kernel<<<cg, 256, 0, s>>>(p.hole, board, n_players, ghost, Q, ws);
+        validate_ranges_kernel<<<cg, 256, 0, s>>>(p.hole, board, n_players, ghost, p.known_opp, n_known, Q, ws);
         uint32_t bad = 0;
         e = cudaMemcpyAsync(&bad, ws + kWsInvalid, 4, cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) return cuda_fail(e, "query validation");
         if (bad) return fail(NPK_ERR_INVALID_CARDS, std::to_string(bad) + " invalid quer" + (bad == 1 ? "y" : "ies") +
-                             " (card id >= 52, duplicate cards, gap in the board, ghost card on the board or in the "
-                             "hand, or players outside 1..10)");
+                             " (card id >= 52, duplicate cards, gap in the board, ghost card on the board or in a "
+                             "hand, more known opponents than opponents, or players outside 1..10)");
     }
     // `passes` is a by-product of the reference's attempt loop: only the generic kernel, which plays that loop literally,
     // can count it; everyone else gets the pair-list sampler (csrc/npk_ranges.cu), which redraws far less often
@@ -1258,6 +1286,15 @@ int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint
                            uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types,
                            uint64_t* passes)
 {
+    return npk_equity_ranges_known_host(hole, board, n_players, ghost, nullptr, 0, Q, trials, opp_allowed, hero_allowed, seed,
+                                        deal_mode, wins_strict, ties, win_types, passes);
+}
+
+int npk_equity_ranges_known_host(const uint8_t* hole, const uint8_t* board, const uint8_t* n_players, const uint8_t* ghost,
+                                 const uint8_t* known_opp, int n_known, int64_t Q, int64_t trials, const uint64_t* opp_allowed,
+                                 const uint64_t* hero_allowed, uint64_t seed, int deal_mode, uint64_t* wins_strict,
+                                 uint64_t* ties, uint64_t* win_types, uint64_t* passes)
+{
     DeviceState* ds;
     int rc = current_state(&ds);
     if (rc) return rc;
@@ -1270,19 +1307,24 @@ int npk_equity_ranges_host(const uint8_t* hole, const uint8_t* board, const uint
     void* d_ws = nullptr;
     cudaError_t e;
     auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws); };
-    if ((e = cudaMalloc(&d_in, 10 * Q)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if (n_known < 0 || n_known > 9 || (n_known > 0 && !known_opp))
+        return fail(NPK_ERR_INVALID_ARGUMENT, "n_known must be 0..9 and known_opp must be given when it is not 0");
+    const int64_t per_q = 10 + 2 * n_known;                                       // bytes of input per query
+    if ((e = cudaMalloc(&d_in, per_q * Q)) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&d_out, 8 * 12 * Q)) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
     if ((e = cudaMalloc(&d_ws, npk_equity_workspace_bytes(Q))) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
-    std::vector<uint8_t> h_in(10 * (size_t)Q, 0xFF);
+    std::vector<uint8_t> h_in((size_t)(per_q * Q), 0xFF);
     if (hole) std::memcpy(h_in.data(), hole, 2 * Q);
     std::memcpy(h_in.data() + 2 * Q, board, 5 * Q);
     std::memcpy(h_in.data() + 7 * Q, n_players, Q);
     if (ghost) std::memcpy(h_in.data() + 8 * Q, ghost, 2 * Q);
-    if ((e = cudaMemcpy(d_in, h_in.data(), 10 * Q, cudaMemcpyHostToDevice)) != cudaSuccess) { cleanup(); return cuda_fail(e, "H2D"); }
+    if (n_known > 0) std::memcpy(h_in.data() + 10 * Q, known_opp, (size_t)(2 * n_known) * Q);
+    if ((e = cudaMemcpy(d_in, h_in.data(), per_q * Q, cudaMemcpyHostToDevice)) != cudaSuccess) { cleanup(); return cuda_fail(e, "H2D"); }
     if ((e = cudaMemset(d_out, 0, 8 * 12 * Q)) != cudaSuccess) { cleanup(); return cuda_fail(e, "memset"); }
-    rc = npk_equity_ranges_batch(hole ? d_in : nullptr, d_in + 2 * Q, d_in + 7 * Q, ghost ? d_in + 8 * Q : nullptr, Q, trials,
-                                 opp_allowed, hero_allowed, seed, 0, 0, deal_mode, NPK_FLAG_VALIDATE, d_out, d_out + Q,
-                                 win_types ? d_out + 2 * Q : nullptr, passes ? d_out + 11 * Q : nullptr, d_ws, nullptr);
+    rc = npk_equity_ranges_known_batch(hole ? d_in : nullptr, d_in + 2 * Q, d_in + 7 * Q, ghost ? d_in + 8 * Q : nullptr,
+                                       n_known > 0 ? d_in + 10 * Q : nullptr, n_known, Q, trials, opp_allowed, hero_allowed, seed,
+                                       0, 0, deal_mode, NPK_FLAG_VALIDATE, d_out, d_out + Q, win_types ? d_out + 2 * Q : nullptr,
+                                       passes ? d_out + 11 * Q : nullptr, d_ws, nullptr);
     if (rc) { cleanup(); return rc; }
     std::vector<uint64_t> h_out(12 * (size_t)Q);
     if ((e = cudaMemcpy(h_out.data(), d_out, 8 * 12 * Q, cudaMemcpyDeviceToHost)) != cudaSuccess) { cleanup(); return cuda_fail(e, "D2H"); }

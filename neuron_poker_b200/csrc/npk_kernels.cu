@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
         const long long q = p.qindex ? p.qindex[qslot] : qslot;
         int known = 0;
         for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
-        const int nopp = (int)p.n_players[q] - 1;
+        // opponents dealt at random; the others' cards are known (montecarlo_python.py:132-163: removed from the deck like the
+        // hero's, part of the showdown like any opponent)
+        const int nknown = (int)p.n_known;
+        const int nopp = max(0, (int)p.n_players[q] - 1 - nknown);
 
         // static part of the query: the known board, the cards nobody can receive
         uint64_t taken = 0;
@@ -116,6 +119,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
             for (int i = 0; i < 2; i++) { const uint8_t c = p.ghost[2 * q + i]; if (c < 52) taken |= 1ull << c; }
         int h0 = 0, h1 = 0;
         if (!p.hero_range) { h0 = p.hole[2 * q]; h1 = p.hole[2 * q + 1]; taken |= (1ull << h0) | (1ull << h1); }
+        for (int f = 0; f < 2 * nknown; f++) taken |= 1ull << (p.known_opp[2 * q * nknown + f] & 63u);
         const uint64_t avail0 = ~taken & ((1ull << 52) - 1ull);
         const int n0 = __popcll(avail0);
 
@@ -185,11 +189,18 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_kernel(const Equ
             uint32_t bfield = prmt(board_lo, board_hi, bf.sel);
             for (int k = 0; k < nbd; k++) bfield |= flush_bit(bd[k], bf.fsx);
             const uint32_t hv = eval_player(st, bsum + hd0 + hd1, bfield | flush_bit(hd0, bf.fsx) | flush_bit(hd1, bf.fsx), bf.thr);
-            if (active)
+            if (active) {
                 for (int o = 0; o < nopp; o++)
                     best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
                                                  bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
-            const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
+                for (int f = 0; f < nknown; f++) {
+                    const uint32_t k1 = p.tables.desc[p.known_opp[2 * (q * nknown + f)] & 63u];
+                    const uint32_t k2 = p.tables.desc[p.known_opp[2 * (q * nknown + f) + 1] & 63u];
+                    best = max(best, eval_player(st, bsum + k1 + k2, bfield | flush_bit(k1, bf.fsx) | flush_bit(k2, bf.fsx), bf.thr));
+                }
+            }
+            const int nrivals = nopp + nknown;
+            const bool win = active && (nrivals == 0 || hv > best), tie = active && nrivals > 0 && hv == best;
             wins += win; ties += tie;
             if (p.win_types && (win || tie)) {
                 uint32_t ty = 0;

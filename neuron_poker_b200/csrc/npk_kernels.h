@@ -113,6 +113,9 @@ struct EquityParams {
     uint32_t hero_mask[6];        // the same for the hero when hero_range != 0
     uint32_t hero_range;          // 1: the hero is drawn from hero_mask every trial (`hole` is not read)
     const uint8_t* ghost;         // [Q,2] cards removed from the deck before dealing (0xFF = none), or null
+    const uint8_t* known_opp;     // [Q,n_known,2] opponents whose cards are known (the reference's several known hands in
+                                  // player_card_list, montecarlo_python.py:132-163), or null
+    uint32_t n_known;             // how many of the n_players - 1 opponents those are
     uint32_t* abort_flag;         // raised when one draw needs more than kMaxRangeAttempts attempts
 };
 

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_fast_kernel(cons
         const long long q = p.qindex ? p.qindex[qslot] : qslot;
         int known = 0;
         for (int i = 0; i < 5; i++) known += p.board[5 * q + i] != 0xFF;
-        const int nopp = (int)p.n_players[q] - 1;
+        const int nknown = (int)p.n_known;                    // opponents whose cards are known (montecarlo_python.py:132-163)
+        const int nopp = max(0, (int)p.n_players[q] - 1 - nknown);
 
         uint64_t taken = 0;
         uint32_t board_sum = 0, board_lo = 0, board_hi = 0, board_cnt = 0x5555u;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_fast_kernel(cons
             for (int i = 0; i < 2; i++) { const uint8_t c = p.ghost[2 * q + i]; if (c < 52) taken |= 1ull << c; }
         uint32_t h0 = 0, h1 = 0;
         if (!p.hero_range) { h0 = p.hole[2 * q] & 63u; h1 = p.hole[2 * q + 1] & 63u; taken |= (1ull << h0) | (1ull << h1); }
+        for (int f = 0; f < 2 * nknown; f++) taken |= 1ull << (p.known_opp[2 * q * nknown + f] & 63u);
         const uint64_t avail0 = ~taken & ((1ull << 52) - 1ull);
         const int n0 = __popcll(avail0);
 
@@ -194,7 +196,13 @@ __global__ void __launch_bounds__(kRefThreads, 1) equity_ranges_fast_kernel(cons
                 if (o < nopp && active)
                     best = max(best, eval_player(st, bsum + oc1[o] + oc2[o],
                                                  bfield | flush_bit(oc1[o], bf.fsx) | flush_bit(oc2[o], bf.fsx), bf.thr));
-            const bool win = active && (nopp == 0 || hv > best), tie = active && nopp > 0 && hv == best;
+            for (int f = 0; f < nknown && active; f++) {
+                const uint32_t k1 = stab.desc[p.known_opp[2 * (q * nknown + f)] & 63u];
+                const uint32_t k2 = stab.desc[p.known_opp[2 * (q * nknown + f) + 1] & 63u];
+                best = max(best, eval_player(st, bsum + k1 + k2, bfield | flush_bit(k1, bf.fsx) | flush_bit(k2, bf.fsx), bf.thr));
+            }
+            const int nrivals = nopp + nknown;
+            const bool win = active && (nrivals == 0 || hv > best), tie = active && nrivals > 0 && hv == best;
             wins += win; ties += tie;
             if (p.win_types && (win || tie)) {
                 uint32_t ty = 0;

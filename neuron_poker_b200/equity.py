@@ -249,12 +249,14 @@ def _u64(a):
 
 
 def equity_counts_ranges(player_cards, table_cards, players, runs, opponent_range=1, ghost_cards='',
-                         deal_mode="reference", seed_value=None):
+                         deal_mode="reference", seed_value=None, known_opponents=()):
     """One run_montecarlo call with ranges through npk_equity_ranges_host (blocking).
 
     player_cards: two card strings, or a SET of class spellings ('AKO', 'AA', ...): the hero is then drawn from that
     range every trial (montecarlo_python.py:136-148).  opponent_range: a fraction of the reference's preflop ranking
     (:36-112) or a set of class spellings (:194-199).  ghost_cards: '' or two cards removed from the deck (:206-208).
+    known_opponents: hands (two card strings each) of opponents whose cards are known -- the further entries of the
+    reference's player_card_list (:132-163); they count among `players`.
     Returns dict(wins, ties, runs, win_types[9], passes)."""
     players, runs = int(players), int(runs)
     if players < 1:
@@ -273,6 +275,20 @@ def equity_counts_ranges(player_cards, table_cards, players, runs, opponent_rang
         hole = card_ids(player_cards)
         if len(hole) != 2:
             raise ValueError("player_cards must hold exactly two cards, got %d" % len(hole))
+    known = []
+    for hand in known_opponents:
+        if isinstance(hand, (set, frozenset)):
+            raise NotImplementedError("a known opponent must be two cards, not a range")
+        ids = card_ids(hand)
+        if len(ids) != 2:
+            raise ValueError("a known opponent's hand must hold exactly two cards, got %d" % len(ids))
+        known += ids
+    n_known = len(known) // 2
+    if n_known and hero_is_range:
+        raise NotImplementedError("a hero range together with known opponent hands (the reference draws the hero before it "
+                                  "removes the known hands and deals duplicate cards, montecarlo_python.py:132-163)")
+    if n_known > players - 1:
+        raise ValueError("more known hands than players")
     opp_mask = ranges.opponent_mask(opponent_range)
     hero_mask = ranges.mask_from_classes(player_cards) if hero_is_range else None
     L = _lib.ensure_init(_device())
@@ -283,11 +299,16 @@ def equity_counts_ranges(player_cards, table_cards, players, runs, opponent_rang
     out_w, out_t = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
     out_ty, out_p = np.zeros(9, dtype=np.uint64), np.zeros(1, dtype=np.uint64)
     s = _next_seed() if seed_value is None else int(seed_value)
-    _lib.check(L.npk_equity_ranges_host(_u8(hole_a) if hole_a is not None else None, _u8(board_a), _u8(npl),
-                                        _u8(ghost_a) if ghost_a is not None else None, 1, runs, _u64(opp_mask),
+    known_a = np.array(known, dtype=np.uint8) if n_known else None
+    rc = L.npk_equity_ranges_known_host(_u8(hole_a) if hole_a is not None else None, _u8(board_a), _u8(npl),
+                                        _u8(ghost_a) if ghost_a is not None else None,
+                                        _u8(known_a) if known_a is not None else None, n_known, 1, runs, _u64(opp_mask),
                                         _u64(hero_mask) if hero_mask is not None else None,
                                         ctypes.c_uint64(s & (2**64 - 1)), _DEAL[deal_mode], _u8(out_w), _u8(out_t),
-                                        _u8(out_ty), _u8(out_p)))
+                                        _u8(out_ty), _u8(out_p))
+    if rc == -5:
+        raise ValueError("duplicate or invalid cards among player / known / table / ghost cards: " + L.npk_last_error().decode())
+    _lib.check(rc)
     return {"wins": int(out_w[0]), "ties": int(out_t[0]), "runs": runs, "win_types": [int(x) for x in out_ty],
             "passes": int(out_p[0])}
 
@@ -315,21 +336,21 @@ class MonteCarlo(object):
     def run_montecarlo(self, original_player_card_list, original_table_card_list, player_amount, ui, maxRuns,
                        timeout, ghost_cards, opponent_range=1):
         """montecarlo_python.py:191-252.  `ui` and `timeout` are accepted and ignored (every run is executed).
-        The plain case (opponent_range=1, a fixed hero, no ghost cards) runs equity_refdeal_kernel; anything else runs
-        the range kernel.  A range no remaining hand can satisfy raises NpkError instead of looping forever."""
-        if len(original_player_card_list) != 1:
-            raise NotImplementedError("exactly one known hand or hero range is supported (the reference's collusion "
-                                      "case of several known hands is not used by any caller)")
+        The plain case (opponent_range=1, one fixed hero, no ghost cards) runs equity_refdeal_kernel; anything else -- ranges,
+        ghost cards, further known hands in the player list -- runs the range kernel.  A range no remaining hand can satisfy raises NpkError instead of looping forever."""
+        if len(original_player_card_list) < 1:
+            raise IndexError("list index out of range")
         hero = original_player_card_list[0]
+        known = list(original_player_card_list[1:])       # further known hands: opponents whose cards are known (:132-163)
         plain = (ghost_cards == '' and not isinstance(opponent_range, (set, frozenset)) and
-                 not isinstance(hero, (set, frozenset)) and
+                 not isinstance(hero, (set, frozenset)) and not known and
                  len(ranges.allowed_classes(opponent_range)) == ranges.N_CLASSES)
         if plain:
             r = equity_counts(hero, original_table_card_list, player_amount, maxRuns, deal_mode="reference",
                               win_types=True, passes=True)
         else:
             r = equity_counts_ranges(hero, original_table_card_list, player_amount, maxRuns, opponent_range=opponent_range,
-                                     ghost_cards=ghost_cards, deal_mode="reference")
+                                     ghost_cards=ghost_cards, deal_mode="reference", known_opponents=known)
         runs = r["runs"]
         self.equity = (r["wins"] + r["ties"]) / runs
         self.winnerCardTypeList = Counter({HAND_TYPES[i]: c / runs for i, c in enumerate(r["win_types"]) if c})
@@ -342,8 +363,9 @@ class MonteCarlo(object):
 # ---- batched API on device tensors -----------------------------------------------------------------------------------
 def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, hero_range=None, ghost=None, seed_value=0,
                             deal_mode="reference", trial_offset=0, query_offset=0, device=None, validate=True,
-                            win_types=False, passes=False, out=None):
+                            win_types=False, passes=False, out=None, known_opponents=None):
     """Batched Monte-Carlo counts with ranges (asynchronous on the current torch stream unless validate=True).
+    known_opponents: None or [Q, n_known, 2] uint8 -- opponents whose cards are known (they count among n_players).
 
     opponent_range: fraction or set of class spellings shared by every query; hero_range: None (fixed `hole` [Q,2]) or a
     set of class spellings (the hero is drawn from it every trial, `hole` may be None); ghost: None or [Q,2] uint8
@@ -355,6 +377,12 @@ def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, he
     Q = board.shape[0]
     hole = None if hero_range is not None else _as_cuda_u8(hole, dev, (2,))
     ghost = None if ghost is None else _as_cuda_u8(ghost, dev, (2,))
+    n_known = 0
+    if known_opponents is not None:
+        known_opponents = torch.as_tensor(known_opponents, dtype=torch.uint8).to(dev).contiguous()
+        if known_opponents.dim() != 3 or known_opponents.shape[0] != Q or known_opponents.shape[2] != 2:
+            raise ValueError("known_opponents must have shape [Q, n_known, 2]")
+        n_known = int(known_opponents.shape[1])
     opp_mask = ranges.opponent_mask(opponent_range)
     hero_mask = None if hero_range is None else ranges.mask_from_classes(hero_range)
     L = _lib.ensure_init(dev.index)
@@ -366,8 +394,9 @@ def get_equity_ranges_batch(hole, board, n_players, trials, opponent_range=1, he
                 out[name] = torch.zeros(shape, dtype=torch.int64, device=dev)
         ws = torch.empty(int(L.npk_equity_workspace_bytes(Q)), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(L.npk_equity_ranges_batch(hole.data_ptr() if hole is not None else None, board.data_ptr(),
-                                             n_players.data_ptr(), ghost.data_ptr() if ghost is not None else None, Q,
+        _lib.check(L.npk_equity_ranges_known_batch(hole.data_ptr() if hole is not None else None, board.data_ptr(),
+                                             n_players.data_ptr(), ghost.data_ptr() if ghost is not None else None,
+                                             known_opponents.data_ptr() if n_known else None, n_known, Q,
                                              int(trials), _u64(opp_mask), _u64(hero_mask) if hero_mask is not None else None,
                                              ctypes.c_uint64(int(seed_value) & (2**64 - 1)), int(trial_offset),
                                              int(query_offset), _DEAL[deal_mode],

@@ -429,7 +429,7 @@ static int class_allowed(const uint64_t *mask, int c1, int c2)
  * out layout as oracle_mc_reference.  Returns -3 when a draw exceeds ORACLE_MAX_ATTEMPTS. */
 int oracle_mc_reference_ranges(const uint8_t *hero, const uint64_t *hero_mask, const uint8_t *board, int nboard,
                                int players, int64_t runs, uint32_t seed, const uint64_t *opp_mask, const uint8_t *ghost,
-                               int64_t *out)
+                               const uint8_t *known, int n_known, int64_t *out)
 {
     oracle_mt_t rng;
     oracle_mt_seed(&rng, seed);
@@ -471,7 +471,16 @@ int oracle_mc_reference_ranges(const uint8_t *hero, const uint64_t *hero_mask, c
             int ix = list_index(deck, n, hole[0][k]);
             if (ix >= 0) list_pop(deck, &n, ix);
         }
-        for (int p = 1; p < players; p++) {                      /* :165-181 */
+        /* further entries of player_card_list: hands that are known (:132-163), removed by value like the hero's
+         * (a failed removal is swallowed, :154-161) */
+        for (int f = 0; f < n_known; f++) {
+            for (int k = 0; k < 2; k++) {
+                hole[1 + f][k] = known[2 * f + k];
+                int ix = list_index(deck, n, known[2 * f + k]);
+                if (ix >= 0) list_pop(deck, &n, ix);
+            }
+        }
+        for (int p = 1 + n_known; p < players; p++) {            /* :165-181 */
             int64_t i1, i2, tries = 0;
             for (;;) {
                 passes++;
@@ -500,7 +509,7 @@ int oracle_mc_reference_ranges(const uint8_t *hero, const uint64_t *hero_mask, c
  * until their class is allowed; the board is uniform.  out[0]=wins_strict out[1]=ties out[2]=attempts. */
 int oracle_mc_uniform_ranges(const uint8_t *hero, const uint64_t *hero_mask, const uint8_t *board, int nboard,
                              int players, int64_t runs, uint32_t seed, const uint64_t *opp_mask, const uint8_t *ghost,
-                             int64_t *out)
+                             const uint8_t *known_cards, int n_known, int64_t *out)
 {
     oracle_mt_t rng;
     oracle_mt_seed(&rng, seed);
@@ -513,12 +522,15 @@ int oracle_mc_uniform_ranges(const uint8_t *hero, const uint64_t *hero_mask, con
             if (!hero_mask) known |= (c == hero[0] || c == hero[1]);
             if (ghost) known |= (c == ghost[0] || c == ghost[1]);
             for (int i = 0; i < nboard; i++) known |= (c == board[i]);
+            for (int f = 0; f < 2 * n_known; f++) known |= (c == known_cards[f]);
             if (!known) deck[n++] = (uint8_t)c;
         }
         uint8_t hole[10][2];
         int first = hero_mask ? 0 : 1;
         if (!hero_mask) { hole[0][0] = hero[0]; hole[0][1] = hero[1]; }
+        for (int f = 0; f < n_known; f++) { hole[1 + f][0] = known_cards[2 * f]; hole[1 + f][1] = known_cards[2 * f + 1]; }
         for (int p = first; p < players; p++) {
+            if (p >= 1 && p <= n_known) continue;                /* a known hand */
             const uint64_t *mk = p == 0 ? hero_mask : opp_mask;
             int64_t tries = 0;
             int i1, i2;

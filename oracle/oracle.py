@@ -56,7 +56,7 @@ def lib():
         u64p = ctypes.POINTER(ctypes.c_uint64)
         for name in ("oracle_mc_reference_ranges", "oracle_mc_uniform_ranges"):
             getattr(L, name).argtypes = [u8p, u64p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32,
-                                         u64p, u8p, i64p]
+                                         u64p, u8p, u8p, ctypes.c_int, i64p]
         L.oracle_hand_class.argtypes = [ctypes.c_int, ctypes.c_int]
         L.oracle_enum_headsup.argtypes = [u8p, u8p, ctypes.c_int, i64p]
         L.oracle_enum_river_multi.argtypes = [u8p, u8p, ctypes.c_int, i64p]
@@ -216,30 +216,34 @@ def class_mask(names):
     return (ctypes.c_uint64 * 3)(*m)
 
 
-def _ranges_call(fn, hero, hero_classes, board, players, runs, seed, opp_classes, ghost):
+def _ranges_call(fn, hero, hero_classes, board, players, runs, seed, opp_classes, ghost, known=()):
     b = ids(board)
     h = ids(hero) if hero_classes is None else None
     g = ids(ghost) if ghost else None
+    k = ids([c for hand in known for c in hand]) if known else None
     out = (ctypes.c_int64 * 12)()
     rc = fn(_p(h) if h is not None else None, class_mask(hero_classes) if hero_classes is not None else None,
             _p(b) if len(b) else None, len(b), int(players), int(runs), int(seed), class_mask(opp_classes),
-            _p(g) if g is not None else None, out)
+            _p(g) if g is not None else None, _p(k) if k is not None else None, len(known), out)
     if rc:
         raise ValueError("oracle ranges call rc=%d" % rc)
     return out
 
 
-def mc_reference_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None):
-    """run_montecarlo with an opponent range (set of class spellings), optionally a hero range and ghost cards, under
-    np.random.seed(seed): dict(wins, passes, win_types, next_randint).  `hero` is ignored when hero_classes is given."""
-    out = _ranges_call(lib().oracle_mc_reference_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost)
+def mc_reference_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None, known=()):
+    """run_montecarlo with an opponent range (set of class spellings), optionally a hero range, ghost cards and further
+    known hands (`known`: the entries of player_card_list after the hero's), under np.random.seed(seed):
+    dict(wins, passes, win_types, next_randint).  `hero` is ignored when hero_classes is given."""
+    out = _ranges_call(lib().oracle_mc_reference_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost,
+                       known)
     return {"wins": out[0], "passes": out[1], "win_types": {CAT_NAMES[i]: out[2 + i] for i in range(9) if out[2 + i]},
             "next_randint": out[11]}
 
 
-def mc_uniform_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None):
+def mc_uniform_ranges(hero, board, players, runs, seed, opp_classes, hero_classes=None, ghost=None, known=()):
     """Unbiased dealing with ranges: (wins_strict, ties, attempts)."""
-    out = _ranges_call(lib().oracle_mc_uniform_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost)
+    out = _ranges_call(lib().oracle_mc_uniform_ranges, hero, hero_classes, board, players, runs, seed, opp_classes, ghost,
+                       known)
     return out[0], out[1], out[2]
 
 

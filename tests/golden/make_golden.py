@@ -19,6 +19,7 @@ Files written (all small, committed):
                        the oracle's MT19937 + legacy randint + dealing restatement bit-exactly
   preflop_order.json   the reference's ranking of the 169 starting-hand classes and the allowed sets of some fractions
   mc_ranges_seeded.json seeded run_montecarlo runs with opponent ranges, hero ranges and ghost cards
+  mc_known_seeded.json  seeded run_montecarlo runs with several known hands in player_card_list (:132-163)
 """
 import argparse
 import hashlib
@@ -406,6 +407,39 @@ def build_ranges():
     print("mc_ranges_seeded.json written")
 
 
+def build_known_hands():
+    """Several known hands in player_card_list (montecarlo_python.py:132-163: the reference's provision for bots sharing a
+    table): the hero's hand first, then hands of opponents whose cards are known; the other opponents are dealt at random."""
+    out = {"source": "MonteCarlo.run_montecarlo under np.random.seed(seed), timeout=+1e9 s, player_card_list = [hero, known "
+                     "hands...]", "numpy": np.__version__, "runs": []}
+    cases = [
+        # name, hero, known hands, board, players, runs, opponent_range, ghost
+        ("known1_flop4", ['AS', 'KS'], [['QH', 'QD']], ['2C', '7D', 'KH'], 4, 1000, 1, ''),
+        ("known2_pre5_r50", ['TS', 'TH'], [['AD', 'KD'], ['7C', '2D']], [], 5, 800, 0.5, ''),
+        ("known1_turn2", ['9D', '9C'], [['AH', 'KC']], ['2C', '7D', 'KH', 'TS'], 2, 1200, 1, ''),
+        ("known1_ghost_set", ['AS', 'KS'], [['JH', 'JD']], ['2C', '7D', 'KH'], 3, 1000, {'AKS', 'KAO', 'QQ', '9TS', 'T9O', '22'},
+         ['AH', 'AD']),
+        ("known3_river6", ['5H', '5D'], [['AD', 'KD'], ['QC', 'QS'], ['8H', '9H']], ['5C', 'KS', '2S', 'TH', 'JH'], 6, 800, 0.3, ''),
+    ]
+    for name, hero, known, board, players, runs, rng, ghost in cases:
+        for seed in (5, 4242):
+            np.random.seed(seed)
+            m = montecarlo_python.MonteCarlo()
+            m.run_montecarlo([list(hero)] + [list(k) for k in known], list(board), players, 1, maxRuns=runs,
+                             timeout=time.time() + 1e9, ghost_cards=ghost, opponent_range=rng)
+            wins = int(round(m.equity * m.runs))
+            types = {k: int(round(v * m.runs)) for k, v in m.winnerCardTypeList.items()}
+            assert sum(types.values()) == wins
+            out["runs"].append({"name": name, "hero": hero, "known": known, "board": board, "players": players, "seed": seed,
+                                "runs": m.runs, "opponent_range": sorted(rng) if isinstance(rng, set) else rng,
+                                "ghost": list(ghost) if ghost else [], "wins": wins, "passes": int(m.passes),
+                                "win_types": types, "next_randint_0_1000000": int(np.random.randint(0, 1000000))})
+        print(" known hands", name, out["runs"][-1]["wins"], "/", runs, "passes", out["runs"][-1]["passes"])
+    with open(os.path.join(HERE, "mc_known_seeded.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("mc_known_seeded.json written")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -421,6 +455,8 @@ def main():
         build_enum(a.quick)
     if not only or "ranges" in only:
         build_ranges()
+    if not only or "known" in only:
+        build_known_hands()
 
 
 if __name__ == "__main__":

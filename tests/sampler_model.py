@@ -160,7 +160,7 @@ def _allowed(mask, c1, c2):
     return (int(mask[k >> 6]) >> (k & 63)) & 1
 
 
-def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None):
+def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None, known=()):
     """equity_ranges_kernel: dealing with an opponent range (169-bit mask, three 64-bit words), optionally a hero drawn
     from a range (`hole` ignored) and ghost cards removed from the deck.  Returns (hero, opponents, full board, passes).
 
@@ -170,8 +170,9 @@ def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_m
                  an opponent gets deck.pop(i1) then deck.pop(i2) from the shortened list; board card j = hi32(w*(n-1)).
       uniform:   c1 = deck[i1], c2 = (deck without c1)[i2], retry while their class is not allowed; board j = hi32(w*n).
     """
-    known = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set())
-    deck = [c for c in range(52) if c not in known]
+    # `known`: hands of opponents whose cards are known (montecarlo_python.py:132-163): out of the deck, part of the showdown
+    seen = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set()) | {c for h in known for c in h}
+    deck = [c for c in range(52) if c not in seen]
     ws = _Words(seed, query, trial)
     ws.blk = RANGES_BLOCK0[mode]
     passes = 0
@@ -204,7 +205,7 @@ def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_m
         raise RuntimeError("range cannot be satisfied")
 
     hero = list(hole) if hero_mask is None else draw(hero_mask, True)
-    opp = [draw(opp_mask, False) for _ in range(players - 1)]
+    opp = [list(h) for h in known] + [draw(opp_mask, False) for _ in range(players - 1 - len(known))]
     full = list(board)
     while len(full) < 5:
         n = len(deck)
@@ -216,7 +217,7 @@ def deal_ranges(mode, seed, query, trial, hole, board, players, opp_mask, hero_m
 FAST_BLOCK0 = {"reference": 0xA0000000, "uniform": 0xE0000000}
 
 
-def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None):
+def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, hero_mask=None, ghost=None, known=()):
     """equity_ranges_fast_kernel (csrc/npk_ranges.cu): the same distribution of dealt cards as deal_ranges without the
     attempt loop over the whole deck.  Per query the unordered pairs (a < b) of initially unseen cards whose class is
     allowed are listed in ascending pair number b*(b-1)/2 + a; a draw takes entry hi32(w * len) and swaps it when bit 31 of
@@ -225,8 +226,8 @@ def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, h
     opponent gets sa and, when sb > sa, the successor of sb among the unseen cards (pop(i1) shifted the list), else sb.
     Board card: index hi32(w * (n-1)) (reference) / hi32(w * n) (uniform) of the ordered unseen cards.  One Philox word per
     attempt / board card, blocks from 0xA0000000 (reference) / 0xE0000000 (uniform).  Returns (hero, opponents, board)."""
-    known = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set())
-    deck0 = [c for c in range(52) if c not in known]
+    seen = set(board) | (set(ghost) if ghost else set()) | (set(hole) if hero_mask is None else set()) | {c for h in known for c in h}
+    deck0 = [c for c in range(52) if c not in seen]
     avail = set(deck0)
     ws = _Words(seed, query, trial)
     ws.blk = FAST_BLOCK0[mode]
@@ -234,7 +235,7 @@ def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, h
     def pair_list(mask):
         return [(a, b) for b in range(1, 52) for a in range(b) if a in avail and b in avail and _allowed(mask, a, b)]
 
-    opp_list = pair_list(opp_mask) if players > 1 else []
+    opp_list = pair_list(opp_mask) if players - 1 - len(known) > 0 else []
     hero_list = pair_list(hero_mask) if hero_mask is not None else []
 
     def draw(lst, is_hero):
@@ -258,7 +259,7 @@ def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, h
         raise RuntimeError("range cannot be satisfied")
 
     hero = list(hole) if hero_mask is None else draw(hero_list, True)
-    opp = [draw(opp_list, False) for _ in range(players - 1)]
+    opp = [list(h) for h in known] + [draw(opp_list, False) for _ in range(players - 1 - len(known))]
     full = list(board)
     while len(full) < 5:
         n = len(avail)
@@ -270,7 +271,7 @@ def deal_ranges_fast(mode, seed, query, trial, hole, board, players, opp_mask, h
 
 
 def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_offset=0, opp_mask=None, hero_mask=None,
-              ghost=None, fast=False):
+              ghost=None, fast=False, known=()):
     """dict(wins, ties, passes, win_types[9]) of the modelled sampler scored by the oracle's rank ids.  With `opp_mask`
     the range dealers (deal_ranges) are modelled, otherwise the plain ones."""
     wins = ties = passes = 0
@@ -278,9 +279,9 @@ def run_model(oracle, mode, seed, query, hole, board, players, trials, trial_off
     for t in range(trial_offset, trial_offset + trials):
         if opp_mask is not None:
             if fast:
-                hole_t, opp, full = deal_ranges_fast(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
+                hole_t, opp, full = deal_ranges_fast(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost, known)
             else:
-                hole_t, opp, full, p = deal_ranges(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost)
+                hole_t, opp, full, p = deal_ranges(mode, seed, query, t, hole, board, players, opp_mask, hero_mask, ghost, known)
                 passes += p
             hv = oracle.rank7(list(hole_t) + full)
             best = max([oracle.rank7(o + full) for o in opp], default=-1)

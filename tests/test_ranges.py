@@ -282,3 +282,109 @@ def test_unsatisfiable_range_is_an_error_not_a_hang(cuda_device):
     with pytest.raises(NpkError) as ei:        # ghost card that is also on the board: list.index fails in the reference
         npk.equity_counts_ranges(['AS', 'AH'], ['2C', '7D', 'KH'], 2, 100, opponent_range=1, ghost_cards=['KH', '3S'])
     assert ei.value.code == -5
+
+
+# ---- several known hands in player_card_list (montecarlo_python.py:132-163) ---------------------------------------------------
+def _golden_known():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "mc_known_seeded.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_reproduces_reference_runs_with_known_hands():
+    """player_card_list = [hero, known hands...]: wins, passes, win types and the RNG stream position of ten seeded runs of the
+    unmodified reference (tests/golden/make_golden.py --only known), bit for bit."""
+    runs = _golden_known()["runs"]
+    assert len(runs) == 10
+    for run in runs:
+        got = oracle.mc_reference_ranges(run["hero"], run["board"], run["players"], run["runs"], run["seed"], _opp_classes(run),
+                                         ghost=run["ghost"] or None, known=run["known"])
+        assert got["wins"] == run["wins"], run["name"]
+        assert got["passes"] == run["passes"], run["name"]
+        assert got["win_types"] == run["win_types"], run["name"]
+        assert got["next_randint"] == run["next_randint_0_1000000"], run["name"]
+
+
+def test_sampler_specifications_with_known_hands_converge_to_the_oracle():
+    """Both range specifications (literal attempt loop and pair list) with known opponent hands agree with the oracle's
+    restatement of the reference at 3.5 sigma on 6,000 trials each."""
+    T = 6000
+    for i, run in enumerate(_golden_known()["runs"][::2]):
+        hero, board = _ids(run["hero"]), _ids(run["board"])
+        known = [_ids(h) for h in run["known"]]
+        ghost = _ids(run["ghost"]) if run["ghost"] else None
+        cls = _opp_classes(run)
+        o = oracle.mc_reference_ranges(run["hero"], run["board"], run["players"], 60000, 3 + i, cls, ghost=run["ghost"] or None,
+                                       known=run["known"])
+        p_or = o["wins"] / 60000
+        for fast in (False, True):
+            m = sampler_model.run_model(oracle, "reference", 50 + i, 0, hero, board, run["players"], T,
+                                        opp_mask=ranges.opponent_mask(cls), ghost=ghost, fast=fast, known=known)
+            p = (m["wins"] + m["ties"]) / T
+            se = (p_or * (1 - p_or) * (1 / T + 1 / 60000)) ** 0.5
+            assert abs(p - p_or) < 3.5 * se + 1e-9, (run["name"], fast, p, p_or, se)
+
+
+@pytest.mark.gpu
+def test_known_hands_kernels_match_their_specifications_and_the_oracle(cuda_device):
+    """Opponents whose cards are known (npk_equity_ranges_known_batch): both range kernels equal their specifications bit for
+    bit in both dealing modes; at 2 M trials they agree with the oracle (reference / unbiased restatement) at 3 sigma."""
+    import neuron_poker_b200 as npk
+    T, off = 96, 500
+    for i, run in enumerate(_golden_known()["runs"][::2]):
+        hero, board = _ids(run["hero"]), _ids(run["board"])
+        known = [_ids(h) for h in run["known"]]
+        ghost = _ids(run["ghost"]) if run["ghost"] else None
+        cls = _opp_classes(run)
+        args = (np.array([hero], dtype=np.uint8), np.array([board + [255] * (5 - len(board))], dtype=np.uint8),
+                np.array([run["players"]], dtype=np.uint8))
+        kw = dict(opponent_range=cls, ghost=None if ghost is None else np.array([ghost], dtype=np.uint8),
+                  known_opponents=np.array([known], dtype=np.uint8))
+        for mode in ("reference", "uniform"):
+            for fast in (False, True):
+                out = npk.get_equity_ranges_batch(*args, T, seed_value=31 + i, deal_mode=mode, trial_offset=off, query_offset=2,
+                                                  win_types=True, passes=not fast, **kw)
+                m = sampler_model.run_model(oracle, mode, 31 + i, 2, hero, board, run["players"], T, trial_offset=off,
+                                            opp_mask=ranges.opponent_mask(cls), ghost=ghost, fast=fast, known=known)
+                got = (int(out["wins"][0]), int(out["ties"][0]), [int(x) for x in out["win_types"][0]])
+                assert got == (m["wins"], m["ties"], m["win_types"]), (run["name"], mode, fast, got, m)
+                if not fast:
+                    assert int(out["passes"][0]) == m["passes"], (run["name"], mode)
+            big, TO = 2_000_000, 200_000
+            out = npk.get_equity_ranges_batch(*args, big, seed_value=900 + i, deal_mode=mode, **kw)
+            p_gpu = (int(out["wins"][0]) + int(out["ties"][0])) / big
+            if mode == "reference":
+                p_or = oracle.mc_reference_ranges(run["hero"], run["board"], run["players"], TO, 17 + i, cls,
+                                                  ghost=run["ghost"] or None, known=run["known"])["wins"] / TO
+            else:
+                w, t, _ = oracle.mc_uniform_ranges(run["hero"], run["board"], run["players"], TO, 17 + i, cls,
+                                                   ghost=run["ghost"] or None, known=run["known"])
+                p_or = (w + t) / TO
+            se = (p_or * (1 - p_or) * (1 / big + 1 / TO)) ** 0.5
+            assert abs(p_gpu - p_or) < 3 * se + 1e-9, (run["name"], mode, p_gpu, p_or, se)
+
+
+@pytest.mark.gpu
+def test_run_montecarlo_with_several_known_hands(cuda_device):
+    """MonteCarlo.run_montecarlo([hero, known hand, ...], ...) -- the reference's call form -- against its own seeded runs at
+    3.5 sigma; error behaviour of the combinations that are not supported."""
+    import neuron_poker_b200 as npk
+    from neuron_poker_b200._lib import NpkError
+    npk.seed(99)
+    sim = npk.MonteCarlo()
+    for run in _golden_known()["runs"][::2]:
+        rng = set(run["opponent_range"]) if isinstance(run["opponent_range"], list) else run["opponent_range"]
+        sim.run_montecarlo([run["hero"]] + run["known"], run["board"], run["players"], 1, maxRuns=200000, timeout=0,
+                           ghost_cards=run["ghost"] or '', opponent_range=rng)
+        p_ref = run["wins"] / run["runs"]
+        se = (max(p_ref * (1 - p_ref), 1e-4) * (1 / 200000 + 1 / run["runs"])) ** 0.5
+        assert abs(sim.equity - p_ref) < 3.5 * se, (run["name"], sim.equity, p_ref, se)
+        assert sim.runs == 200000 and abs(sum(sim.winnerCardTypeList.values()) - sim.equity) < 1e-9
+    npk.seed(None)
+    with pytest.raises(NotImplementedError):
+        sim.run_montecarlo([{'AKO', 'AA'}, ['QH', 'QD']], [], 3, 1, maxRuns=100, timeout=0, ghost_cards='')
+    with pytest.raises(ValueError):
+        sim.run_montecarlo([['AS', 'KS'], ['AS', 'QD']], [], 3, 1, maxRuns=100, timeout=0, ghost_cards='')      # a card twice
+    with pytest.raises(ValueError):
+        sim.run_montecarlo([['AS', 'KS'], ['QH', 'QD'], ['JH', 'JD']], [], 2, 1, maxRuns=100, timeout=0, ghost_cards='')
