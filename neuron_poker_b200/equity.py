@@ -306,8 +306,6 @@ def equity_counts_ranges(player_cards, table_cards, players, runs, opponent_rang
                                         _u64(hero_mask) if hero_mask is not None else None,
                                         ctypes.c_uint64(s & (2**64 - 1)), _DEAL[deal_mode], _u8(out_w), _u8(out_t),
                                         _u8(out_ty), _u8(out_p))
-    if rc == -5:
-        raise ValueError("duplicate or invalid cards among player / known / table / ghost cards: " + L.npk_last_error().decode())
     _lib.check(rc)
     return {"wins": int(out_w[0]), "ties": int(out_t[0]), "runs": runs, "win_types": [int(x) for x in out_ty],
             "passes": int(out_p[0])}

@@ -384,7 +384,8 @@ def test_run_montecarlo_with_several_known_hands(cuda_device):
     npk.seed(None)
     with pytest.raises(NotImplementedError):
         sim.run_montecarlo([{'AKO', 'AA'}, ['QH', 'QD']], [], 3, 1, maxRuns=100, timeout=0, ghost_cards='')
-    with pytest.raises(ValueError):
+    with pytest.raises(NpkError) as ei:
         sim.run_montecarlo([['AS', 'KS'], ['AS', 'QD']], [], 3, 1, maxRuns=100, timeout=0, ghost_cards='')      # a card twice
+    assert ei.value.code == -5
     with pytest.raises(ValueError):
         sim.run_montecarlo([['AS', 'KS'], ['QH', 'QD'], ['JH', 'JD']], [], 2, 1, maxRuns=100, timeout=0, ghost_cards='')

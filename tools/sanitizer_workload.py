@@ -100,6 +100,13 @@ for mode in ("reference", "uniform"):
 mc = npk.MonteCarlo()
 mc.run_montecarlo([["AS", "KS"]], ["2C", "7D", "KH"], 3, 1, 500, 0, ghost_cards=["2D", "3D"], opponent_range=0.2)
 print("ok run_montecarlo with ranges", mc.equity, flush=True)
+mc.run_montecarlo([["AS", "KS"], ["QH", "QD"], ["7C", "2D"]], ["2C", "7D", "KH"], 5, 1, 500, 0, ghost_cards='', opponent_range=0.5)
+kn = np.tile(np.array([[[40, 41], [2, 7]]], dtype=np.uint8), (6, 1, 1))
+ho2 = np.tile(np.array([[51, 47]], dtype=np.uint8), (6, 1)); bo2 = np.full((6, 5), 255, dtype=np.uint8)
+for mode in ("reference", "uniform"):
+    check(npk.get_equity_ranges_batch(ho2, bo2, np.full(6, 4, dtype=np.uint8), 400, opponent_range=0.4, seed_value=6,
+                                      deal_mode=mode, known_opponents=kn, passes=mode == "reference"), 400, "known hands " + mode)
+print("ok known opponent hands", mc.equity, flush=True)
 
 # vectorised HoldemTable: self-play with both dealers, observation vector, showdowns
 tb = HoldemTables(96, n_players=6, seed=3, autoplay=[1] * 6)
