@@ -406,9 +406,11 @@ def run_selfplay(args, wl, cx, deal, steps=None):
         step(False)                                 # the first timed step (a 60-step leg is 70 ms long)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         step(True)
     e1.record()
+    host_ms = 1e3 * (time.perf_counter() - h0)      # what the host needed to enqueue the timed steps
     torch.cuda.synchronize()
     clocks = sampler.stop()
     dev_ms = cx.max_over_ranks(e0.elapsed_time(e1))
@@ -430,6 +432,7 @@ def run_selfplay(args, wl, cx, deal, steps=None):
                    "table_actions_per_s": float(tot[1].item()) / (dev_ms * 1e-3),
                    "mean_players_per_query": float(tot[0].item()) / max(1.0, float(tot[1].item()) * runs),
                    "hands_played_per_table": float(st["hands_played"].mean()), "table_errors": int((st["error"] != 0).sum()),
+                   "host_enqueue_ms_per_step": host_ms / steps,
                    "l2": "state (50 MB per rank) streams through L2 every step; not flushed"},
         "clocks": clocks,
         "e2e": {"value": e2e_evals / e2e_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8 * N,
