@@ -180,6 +180,7 @@ int npk_equity_one(uint64_t packed, int players, int64_t trials, uint64_t seed, 
  * The kernel leaves on its own when no query has arrived for `idle_us` microseconds (<= 0: 200; at most 100,000) and is
  * started again by the next query, so it never holds the device for longer than that on its own; while it is resident, other
  * work submitted to the device waits for the SMs it occupies (libnpk's own host entry points of this thread stop it first).
+ * One server per device and process: npk_resident_start fails (NPK_ERR_INVALID_ARGUMENT) while another thread runs one there.
  * npk_resident_stop makes the thread's calls launch a kernel per call again.  Both synchronise with the server only. */
 int npk_resident_start(int ctas, int idle_us);
 int npk_resident_stop(void);

@@ -38,6 +38,10 @@ DeviceState g_dev[kMaxDevices];
 
 // host-staging state of npk_equity_host: one per CALLING THREAD (its own stream, pinned buffers and one-query scratch), so
 // the host entry point is re-entrant -- two host threads never share a stream, a counter or a result block
+// One resident server per device and process: a second one could not get the SMs the first one holds and its requests would
+// starve.  Owner = address of the owning thread's staging block, 0 = none.
+std::atomic<uintptr_t> g_resident_owner[kMaxDevices];
+
 // One batch in flight through the host entry points: its own pinned staging, device buffers, workspace, stream and "done"
 // event, so that the copies and the host-side work of batch i+1 overlap the kernel of batch i (npk_equity_host_submit / _wait).
 struct HostSlot {
@@ -90,6 +94,10 @@ struct HostStage {
         if (cudaGetDevice(&cur) != cudaSuccess) { device = -1; return; }     // runtime already torn down
         cudaSetDevice(device);
         stop_resident();
+        if (res_enabled && device < kMaxDevices) {
+            uintptr_t mine = reinterpret_cast<uintptr_t>(this);
+            g_resident_owner[device].compare_exchange_strong(mine, 0);
+        }
         cudaFree(res_state); cudaFreeHost(res_mb);
         for (HostSlot& s : slot) {
             if (s.stream) cudaStreamSynchronize(s.stream);
@@ -120,6 +128,15 @@ void HostStage::stop_resident()
     }
     cudaStreamSynchronize(stream);            // the kernel itself has ended (bounded by its idle limit in any case)
     res_running = false;
+}
+
+// give the device's resident slot back (the thread stops serving its calls through a server)
+static void release_resident_slot(HostStage& st)
+{
+    if (st.device >= 0 && st.device < kMaxDevices) {
+        uintptr_t mine = reinterpret_cast<uintptr_t>(&st);
+        g_resident_owner[st.device].compare_exchange_strong(mine, 0);
+    }
 }
 
 // Tuning aids, read from the environment ONCE (a getenv per launch costs as much as the launch of a 30 us call).
@@ -988,6 +1005,13 @@ int npk_resident_start(int ctas, int idle_us)
     if (ctas > 255) ctas = 255;                              // the CTA count of the packed accumulator has 8 bits
     if (idle_us <= 0) idle_us = 200;
     if (idle_us > 100000) idle_us = 100000;                  // the kernel must never hold the device for long on its own
+    if (st->device >= 0 && st->device < kMaxDevices) {
+        uintptr_t none = 0;
+        const uintptr_t mine = reinterpret_cast<uintptr_t>(st);
+        if (!g_resident_owner[st->device].compare_exchange_strong(none, mine) && none != mine)
+            return fail(NPK_ERR_INVALID_ARGUMENT, "another thread of this process already runs the resident server on this device "
+                                                  "(one per device: a second one could not get the SMs the first one holds)");
+    }
     st->stop_resident();
     st->res_ctas = ctas;
     st->res_idle_cycles = (long long)idle_us * ds->clock_khz / 1000;
@@ -1004,6 +1028,7 @@ int npk_resident_stop(void)
     if ((rc = thread_stage(&st))) return rc;
     st->res_enabled = false;
     st->stop_resident();
+    release_resident_slot(*st);
     return NPK_OK;
 }
 

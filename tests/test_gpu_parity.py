@@ -661,3 +661,34 @@ def test_resident_server_equals_launch_per_call(torch_mod):
         assert (b1["wins"] == b2["wins"]).all() and (b1["ties"] == b2["ties"]).all()
     finally:
         npk.resident(False)
+
+
+def test_one_resident_server_per_device(torch_mod):
+    """A second host thread cannot start a resident server on a device that already has one (its kernel could not get the SMs
+    the first one holds); it can once the first thread has stopped its own; its launched calls work throughout."""
+    import threading
+    from neuron_poker_b200._lib import NpkError
+    want = npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 5000, deal_mode="uniform", seed_value=1)
+    res = {}
+
+    def other(tag):
+        try:
+            npk.resident(True)
+            res[tag] = "started"
+            res[tag + "_counts"] = npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 5000, deal_mode="uniform", seed_value=1)
+            npk.resident(False)
+        except NpkError as exc:
+            res[tag] = exc.code
+            res[tag + "_counts"] = npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 5000, deal_mode="uniform", seed_value=1)
+
+    try:
+        npk.resident(True, idle_us=2000)
+        t = threading.Thread(target=other, args=("while",))
+        t.start(); t.join()
+        assert res["while"] == -2 and res["while_counts"] == want
+        assert npk.equity_counts({"AS", "KS"}, {"2C", "7D", "KH"}, 6, 5000, deal_mode="uniform", seed_value=1) == want
+    finally:
+        npk.resident(False)
+    t = threading.Thread(target=other, args=("after",))
+    t.start(); t.join()
+    assert res["after"] == "started" and res["after_counts"] == want
