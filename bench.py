@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if self.nv is None:
+        if self.nv is None or os.environ.get("NPK_BENCH_NO_SAMPLER") == "1":      # (debugging aid: no NVML calls at all)
             return
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
@@ -388,9 +388,12 @@ def run_selfplay(args, wl, cx, deal, steps=None):
 
     def step(count):
         tb.selfplay_step(agents, runs=runs, deal_mode=deal)
+        _, _, npl, active = tb._q
+        # players of the query, 0 for a table without a query.  Warm-up steps do the same into the last row (overwritten
+        # later): the first launch of this torch kernel in a process loads its module, which on a freshly started box cost
+        # the timed window 8 ms when only timed steps recorded (1.10 instead of 1.03 ms per step in the first process)
+        torch.mul(npl, active, out=rec[cursor[0] if count else -1])
         if count:
-            _, _, npl, active = tb._q
-            torch.mul(npl, active, out=rec[cursor[0]])          # players of the query, 0 for a table without a query
             cursor[0] += 1
 
     def totals(lo, hi):
