@@ -692,3 +692,32 @@ def test_one_resident_server_per_device(torch_mod):
     t = threading.Thread(target=other, args=("after",))
     t.start(); t.join()
     assert res["after"] == "started" and res["after_counts"] == want
+
+
+def test_rank7_quad_path_agrees_with_the_scalar_path_and_the_oracle(torch_mod):
+    """rank7_kernel evaluates four hands per thread from seven aligned words (the quad loop) and falls back to one hand per
+    thread for an unaligned batch and for the last n % 4 hands.  One million hands through both, a flush-heavy batch included
+    (every third hand: the divergent flush branch in nearly every lane), and a sample against the oracle."""
+    torch = torch_mod
+    rng = np.random.default_rng(12)
+    n = 1_000_003
+    base = rng.random((n, 52)).argsort(1)[:, :7].astype(np.uint8)
+    # every third hand gets five cards of one suit
+    suits = rng.integers(0, 4, n)
+    ranks = rng.random((n, 13)).argsort(1)[:, :5]
+    fl = (4 * ranks + suits[:, None]).astype(np.uint8)
+    heavy = base.copy()
+    sel = np.arange(n) % 3 == 0
+    other = np.array([[(4 * r + (s + 1) % 4) for r in (0, 1)] for s in range(4)], dtype=np.uint8)      # two cards of the next suit
+    heavy[sel, :5] = fl[sel]
+    heavy[sel, 5:] = other[suits[sel]]
+    for cards in (base, heavy):
+        dev = torch.as_tensor(cards).cuda()
+        quad = npk.rank7(dev).cpu().numpy()
+        flat = torch.zeros(7 * n + 1, dtype=torch.uint8, device="cuda")
+        flat[1:] = dev.reshape(-1)
+        scalar = npk.rank7(flat[1:].view(n, 7)).cpu().numpy()                  # pointer % 4 == 1: the scalar path
+        assert (quad == scalar).all()
+        idx = rng.integers(0, n, 60000)
+        assert (quad[idx] == oracle.rank7_batch(cards[idx])).all()
+        assert (quad >= 3225).sum() >= (n // 3 if cards is heavy else n // 50)  # flushes and better are really in there
