@@ -717,10 +717,13 @@ int resident_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const ui
     return NPK_OK;
 }
 
-// One query, one kernel launch, nothing else: the query travels in the kernel parameters, the counters stay in device memory
-// between calls (the last warp hands them over and zeroes them), the result lands in mapped host memory together with the
-// call's sequence number, and the host spins on that number instead of asking the driver to synchronise the stream.
-// No H2D / D2H copy, no memset, no cudaStreamSynchronize on the fast path.
+// One query from the host.  Three ways, all without H2D / D2H copies, memsets or cudaStreamSynchronize on the fast path, all
+// publishing the counters together with the call's sequence number in mapped host memory, where the host spins on that number:
+//   * resident mode on: post the query in the mailbox of this thread's persistent server (resident_query above);
+//   * wins and ties only (what get_equity needs): ONE launch of equity_oneshot_kernel, query in the kernel parameters, one packed
+//     atomic per CTA, one 16-byte store (csrc/npk_mixed.cu);
+//   * win types / passes wanted (or NPK_NO_ONESHOT): one launch of the shape's own kernel; the counters stay in device memory
+//     between calls, the last warp of the grid hands them over and zeroes them (finish_single_call, csrc/npk_mc.cuh).
 int single_query(DeviceState* ds, HostStage& st, const uint8_t* hole, const uint8_t* board, int players, int64_t trials,
                  uint64_t seed, int deal_mode, uint64_t* wins_strict, uint64_t* ties, uint64_t* win_types, uint64_t* passes)
 {
